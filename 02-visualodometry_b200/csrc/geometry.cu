@@ -1,0 +1,662 @@
+// geometry.cu — batched per-correspondence geometry kernels on sm_100a.
+//
+//   vo_triangulate         Cam::triangulatePoints (reference src/cam.cpp:94-140): OpenCV's DLT
+//                          (4x4 system in double, right singular vector of sigma_min) per pair,
+//                          float32 dehomogenisation (convertPointsFromHomogeneous).
+//   vo_essential_recover   Cam::computeEssentialAndRecoverPose (src/cam.cpp:37-91): essential
+//                          matrix from all matches (normalised 8-point, moments reduced on the
+//                          GPU) + OpenCV recoverPose (decomposeEssentialMat, 4 candidates,
+//                          per-correspondence cheirality vote).
+//   vo_project_points      Camera::projectPoints (src/camera.cpp:14-35).
+//   vo_anti_join           add_new_world_points (src/my_utilities.cpp:413-434).
+//
+// These are latency / FP64-issue bound, not HBM bound: one thread per correspondence, no shared
+// staging; small dense solves (9x9 eigen, 3x3 SVD) run on one thread between the data-parallel
+// passes so nothing returns to the host mid-pipeline.
+#include "vo_common.cuh"
+
+#include <float.h>
+#include <math.h>
+
+namespace {
+
+// ---------------------------------------------------------------- small dense LA (double)
+// One-sided (Hestenes) Jacobi SVD of an M x N matrix held in registers/local memory:
+// A <- U*Sigma (columns orthogonal), V accumulates right singular vectors, w = singular values
+// sorted descending.
+template <int M, int N>
+__device__ void jacobi_svd_dev(double (&A)[M][N], double (&V)[N][N], double (&w)[N]) {
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+#pragma unroll
+    for (int j = 0; j < N; ++j) V[i][j] = (i == j) ? 1.0 : 0.0;
+  const double eps = 4 * DBL_EPSILON;
+  for (int sweep = 0; sweep < 80; ++sweep) {
+    bool changed = false;
+#pragma unroll
+    for (int i = 0; i < N - 1; ++i)
+#pragma unroll
+      for (int j = i + 1; j < N; ++j) {
+        double a = 0, b = 0, p = 0;
+#pragma unroll
+        for (int k = 0; k < M; ++k) {
+          a += A[k][i] * A[k][i];
+          b += A[k][j] * A[k][j];
+          p += A[k][i] * A[k][j];
+        }
+        if (fabs(p) <= eps * sqrt(a * b) || p == 0.0) continue;
+        changed = true;
+        const double zeta = (b - a) / (2 * p);
+        const double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1 + zeta * zeta));
+        const double c = 1 / sqrt(1 + t * t), s = c * t;
+#pragma unroll
+        for (int k = 0; k < M; ++k) {
+          const double x = A[k][i], y = A[k][j];
+          A[k][i] = c * x - s * y;
+          A[k][j] = s * x + c * y;
+        }
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+          const double x = V[k][i], y = V[k][j];
+          V[k][i] = c * x - s * y;
+          V[k][j] = s * x + c * y;
+        }
+      }
+    if (!changed) break;
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    double s = 0;
+#pragma unroll
+    for (int k = 0; k < M; ++k) s += A[k][i] * A[k][i];
+    w[i] = sqrt(s);
+  }
+#pragma unroll
+  for (int i = 0; i < N - 1; ++i) {
+#pragma unroll
+    for (int k = i + 1; k < N; ++k) {
+      if (w[k] > w[i]) {  // exchange sort keeps everything in registers
+        double t = w[i]; w[i] = w[k]; w[k] = t;
+#pragma unroll
+        for (int r = 0; r < M; ++r) { t = A[r][i]; A[r][i] = A[r][k]; A[r][k] = t; }
+#pragma unroll
+        for (int r = 0; r < N; ++r) { t = V[r][i]; V[r][i] = V[r][k]; V[r][k] = t; }
+      }
+    }
+  }
+}
+
+// OpenCV DLT: rows x*P[2]-P[0], y*P[2]-P[1] per view; X = null vector of the 4x4 system
+__device__ __forceinline__ void dlt_point_dev(const double* __restrict__ P1, const double* __restrict__ P2,
+                                              double x1, double y1, double x2, double y2, double (&X)[4]) {
+  double A[4][4], V[4][4], w[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    A[0][k] = x1 * P1[8 + k] - P1[k];
+    A[1][k] = y1 * P1[8 + k] - P1[4 + k];
+    A[2][k] = x2 * P2[8 + k] - P2[k];
+    A[3][k] = y2 * P2[8 + k] - P2[4 + k];
+  }
+  jacobi_svd_dev<4, 4>(A, V, w);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) X[k] = V[k][3];
+}
+
+struct ProjPair { double P1[12], P2[12]; };
+
+__global__ void __launch_bounds__(128) triangulate_kernel(ProjPair pp, const float2* __restrict__ x1,
+                                                          const float2* __restrict__ x2, long long n,
+                                                          float* __restrict__ xyz) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float2 a = __ldg(x1 + i), b = __ldg(x2 + i);
+  double X[4];
+  dlt_point_dev(pp.P1, pp.P2, a.x, a.y, b.x, b.y, X);
+  const float X0 = (float)X[0], X1 = (float)X[1], X2 = (float)X[2], X3 = (float)X[3];
+  const float scale = (X3 != 0.f) ? __fdiv_rn(1.f, X3) : 1.f;  // convertPointsFromHomogeneous
+  xyz[3 * i] = __fmul_rn(X0, scale);
+  xyz[3 * i + 1] = __fmul_rn(X1, scale);
+  xyz[3 * i + 2] = __fmul_rn(X2, scale);
+}
+
+// ---------------------------------------------------------------- essential: moments pass
+constexpr int kMom = 45;  // upper triangle of the 9x9 moment matrix sum r r^T
+constexpr int kEssThreads = 128;
+
+struct EssCam { double fx, fy, cx, cy; };
+
+__global__ void __launch_bounds__(kEssThreads) essential_moments_kernel(EssCam cam, const float2* __restrict__ x1,
+                                                                       const float2* __restrict__ x2, long long n,
+                                                                       double* __restrict__ partials) {
+  double m[kMom];
+#pragma unroll
+  for (int k = 0; k < kMom; ++k) m[k] = 0.0;
+  for (long long i = (long long)blockIdx.x * kEssThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kEssThreads) {
+    const float2 p = __ldg(x1 + i), q = __ldg(x2 + i);
+    const double a0 = ((double)p.x - cam.cx) / cam.fx, a1 = ((double)p.y - cam.cy) / cam.fy;
+    const double b0 = ((double)q.x - cam.cx) / cam.fx, b1 = ((double)q.y - cam.cy) / cam.fy;
+    const double r[9] = {b0 * a0, b0 * a1, b0, b1 * a0, b1 * a1, b1, a0, a1, 1.0};
+    int k = 0;
+#pragma unroll
+    for (int u = 0; u < 9; ++u)
+#pragma unroll
+      for (int v = u; v < 9; ++v, ++k) m[k] += r[u] * r[v];
+  }
+  __shared__ double s[kEssThreads / 32][kMom];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < kMom; ++k) {
+    double v = m[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) s[warp][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < kMom) {
+    double v = 0;
+    for (int w = 0; w < kEssThreads / 32; ++w) v += s[w][threadIdx.x];
+    partials[(size_t)blockIdx.x * kMom + threadIdx.x] = v;
+  }
+}
+
+struct EssState {
+  double E[9];
+  double R1[9], R2[9], t[3];  // decomposeEssentialMat
+  double R[9], tt[3];         // recoverPose result
+  int good[4];
+  int pick;
+  int n_good;
+};
+
+__device__ void mm3_dev(const double* A, const double* B, double* C) {
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      double s = 0;
+      for (int k = 0; k < 3; ++k) s += A[3 * i + k] * B[3 * k + j];
+      C[3 * i + j] = s;
+    }
+}
+
+__device__ double det3_dev(const double* M) {
+  return M[0] * (M[4] * M[8] - M[5] * M[7]) - M[1] * (M[3] * M[8] - M[5] * M[6]) + M[2] * (M[3] * M[7] - M[4] * M[6]);
+}
+
+// E = U diag(w) V^T with U completed to a full orthogonal basis
+__device__ void svd3_dev(const double* E, double* U, double* w, double* V) {
+  double A[3][3], Vm[3][3], ww[3];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) A[i][j] = E[3 * i + j];
+  jacobi_svd_dev<3, 3>(A, Vm, ww);
+  double u[3][3];
+  for (int j = 0; j < 2; ++j)
+    for (int k = 0; k < 3; ++k) u[j][k] = (ww[j] > 0) ? A[k][j] / ww[j] : 0.0;
+  u[2][0] = u[0][1] * u[1][2] - u[0][2] * u[1][1];
+  u[2][1] = u[0][2] * u[1][0] - u[0][0] * u[1][2];
+  u[2][2] = u[0][0] * u[1][1] - u[0][1] * u[1][0];
+  for (int j = 0; j < 3; ++j)
+    for (int k = 0; k < 3; ++k) {
+      U[3 * k + j] = u[j][k];
+      V[3 * k + j] = Vm[k][j];
+    }
+  for (int j = 0; j < 3; ++j) w[j] = ww[j];
+}
+
+// cyclic two-sided Jacobi on a symmetric 9x9 matrix; returns the eigenvector of the smallest eigenvalue
+__device__ void smallest_eigvec9(double (&S)[9][9], double (&vec)[9]) {
+  double V[9][9];
+  for (int i = 0; i < 9; ++i)
+    for (int j = 0; j < 9; ++j) V[i][j] = (i == j) ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    double off = 0, diag = 0;
+    for (int i = 0; i < 9; ++i) {
+      diag += S[i][i] * S[i][i];
+      for (int j = i + 1; j < 9; ++j) off += S[i][j] * S[i][j];
+    }
+    if (off <= 1e-32 * diag) break;
+    for (int p = 0; p < 8; ++p)
+      for (int q = p + 1; q < 9; ++q) {
+        const double apq = S[p][q];
+        if (apq == 0.0) continue;
+        const double theta = (S[q][q] - S[p][p]) / (2 * apq);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1));
+        const double c = 1 / sqrt(t * t + 1), s = t * c;
+        for (int k = 0; k < 9; ++k) {
+          const double x = S[k][p], y = S[k][q];
+          S[k][p] = c * x - s * y;
+          S[k][q] = s * x + c * y;
+        }
+        for (int k = 0; k < 9; ++k) {
+          const double x = S[p][k], y = S[q][k];
+          S[p][k] = c * x - s * y;
+          S[q][k] = s * x + c * y;
+        }
+        for (int k = 0; k < 9; ++k) {
+          const double x = V[k][p], y = V[k][q];
+          V[k][p] = c * x - s * y;
+          V[k][q] = s * x + c * y;
+        }
+      }
+  }
+  int best = 0;
+  for (int i = 1; i < 9; ++i)
+    if (S[i][i] < S[best][best]) best = i;
+  for (int k = 0; k < 9; ++k) vec[k] = V[k][best];
+}
+
+// partial moments -> normalised 8-point -> essential projection -> decomposeEssentialMat. One thread.
+__global__ void essential_solve_kernel(const double* __restrict__ partials, int n_blocks, EssState* st) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double m[kMom];
+  for (int k = 0; k < kMom; ++k) {
+    double v = 0;
+    for (int b = 0; b < n_blocks; ++b) v += partials[(size_t)b * kMom + k];
+    m[k] = v;
+  }
+  double S[9][9];
+  {
+    int k = 0;
+    for (int u = 0; u < 9; ++u)
+      for (int v = u; v < 9; ++v, ++k) S[u][v] = S[v][u] = m[k];
+  }
+  // RMS-isotropic Hartley normalisation derived from the moments themselves:
+  // r = x2 (x) x1 with x = (x, y, 1): sums of x1 live in row 8 of S, second moments on the diagonal
+  const double n = S[8][8];
+  const double m1x = S[6][8] / n, m1y = S[7][8] / n, m2x = S[2][8] / n, m2y = S[5][8] / n;
+  const double v1 = (S[6][6] + S[7][7]) / n - (m1x * m1x + m1y * m1y);
+  const double v2 = (S[2][2] + S[5][5]) / n - (m2x * m2x + m2y * m2y);
+  const double s1 = sqrt(2.0 / v1), s2 = sqrt(2.0 / v2);
+  const double T1[9] = {s1, 0, -s1 * m1x, 0, s1, -s1 * m1y, 0, 0, 1};
+  const double T2[9] = {s2, 0, -s2 * m2x, 0, s2, -s2 * m2y, 0, 0, 1};
+  double Kr[9][9];  // T2 (x) T1
+  for (int a = 0; a < 3; ++a)
+    for (int b = 0; b < 3; ++b)
+      for (int c = 0; c < 3; ++c)
+        for (int d = 0; d < 3; ++d) Kr[3 * a + b][3 * c + d] = T2[3 * a + c] * T1[3 * b + d];
+  double tmp[9][9], Sh[9][9];
+  for (int i = 0; i < 9; ++i)
+    for (int j = 0; j < 9; ++j) {
+      double s = 0;
+      for (int k = 0; k < 9; ++k) s += Kr[i][k] * S[k][j];
+      tmp[i][j] = s;
+    }
+  for (int i = 0; i < 9; ++i)
+    for (int j = i; j < 9; ++j) {
+      double s = 0;
+      for (int k = 0; k < 9; ++k) s += tmp[i][k] * Kr[j][k];
+      Sh[i][j] = Sh[j][i] = s;
+    }
+  double f[9];
+  smallest_eigvec9(Sh, f);
+  // E0 = T2^T Fh T1
+  const double T2t[9] = {T2[0], T2[3], T2[6], T2[1], T2[4], T2[7], T2[2], T2[5], T2[8]};
+  double t9[9], E0[9];
+  mm3_dev(T2t, f, t9);
+  mm3_dev(t9, T1, E0);
+  double U[9], w[3], V[9];
+  svd3_dev(E0, U, w, V);
+  double E[9];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) E[3 * i + j] = U[3 * i] * V[3 * j] + U[3 * i + 1] * V[3 * j + 1];
+  int big = 0;
+  for (int k = 1; k < 9; ++k)
+    if (fabs(E[k]) > fabs(E[big])) big = k;
+  if (E[big] < 0)
+    for (int k = 0; k < 9; ++k) E[k] = -E[k];
+  for (int k = 0; k < 9; ++k) st->E[k] = E[k];
+  // decomposeEssentialMat
+  double Vt[9];
+  svd3_dev(E, U, w, V);
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) Vt[3 * i + j] = V[3 * j + i];
+  if (det3_dev(U) < 0)
+    for (int k = 0; k < 9; ++k) U[k] = -U[k];
+  if (det3_dev(Vt) < 0)
+    for (int k = 0; k < 9; ++k) Vt[k] = -Vt[k];
+  const double Wm[9] = {0, 1, 0, -1, 0, 0, 0, 0, 1};
+  const double Wt[9] = {0, -1, 0, 1, 0, 0, 0, 0, 1};
+  double UW[9];
+  mm3_dev(U, Wm, UW);
+  mm3_dev(UW, Vt, st->R1);
+  mm3_dev(U, Wt, UW);
+  mm3_dev(UW, Vt, st->R2);
+  st->t[0] = U[2];
+  st->t[1] = U[5];
+  st->t[2] = U[8];
+  for (int c = 0; c < 4; ++c) st->good[c] = 0;
+}
+
+// recoverPose's cheirality vote: each correspondence triangulated against the 4 candidates
+__global__ void __launch_bounds__(128) essential_cheirality_kernel(EssCam cam, const float2* __restrict__ x1,
+                                                                  const float2* __restrict__ x2, long long n,
+                                                                  EssState* st, unsigned char* __restrict__ masks) {
+  __shared__ double sR[2][9];
+  __shared__ double sT[3];
+  if (threadIdx.x < 9) {
+    sR[0][threadIdx.x] = st->R1[threadIdx.x];
+    sR[1][threadIdx.x] = st->R2[threadIdx.x];
+  }
+  if (threadIdx.x < 3) sT[threadIdx.x] = st->t[threadIdx.x];
+  __syncthreads();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const double dist_thr = 50.0;
+  const double P0[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+  int ok[4] = {0, 0, 0, 0};
+  if (i < n) {
+    const float2 p = __ldg(x1 + i), q = __ldg(x2 + i);
+    const double a0 = ((double)p.x - cam.cx) / cam.fx, a1 = ((double)p.y - cam.cy) / cam.fy;
+    const double b0 = ((double)q.x - cam.cx) / cam.fx, b1 = ((double)q.y - cam.cy) / cam.fy;
+    for (int c = 0; c < 4; ++c) {
+      const double* R = sR[c & 1];
+      const double sg = (c < 2) ? 1.0 : -1.0;
+      double P[12];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        P[4 * r] = R[3 * r];
+        P[4 * r + 1] = R[3 * r + 1];
+        P[4 * r + 2] = R[3 * r + 2];
+        P[4 * r + 3] = sg * sT[r];
+      }
+      double Q[4];
+      dlt_point_dev(P0, P, a0, a1, b0, b1, Q);
+      bool good = Q[2] * Q[3] > 0;
+      const double q0 = Q[0] / Q[3], q1 = Q[1] / Q[3], q2 = Q[2] / Q[3];
+      good = good && (q2 < dist_thr);
+      const double z2 = P[8] * q0 + P[9] * q1 + P[10] * q2 + P[11];
+      good = good && (z2 > 0) && (z2 < dist_thr);
+      ok[c] = good;
+      masks[(size_t)c * n + i] = good ? 255 : 0;
+    }
+  }
+  for (int c = 0; c < 4; ++c) {
+    const int cnt = __syncthreads_count(ok[c]);
+    if (threadIdx.x == 0 && cnt) atomicAdd(&st->good[c], cnt);
+  }
+}
+
+__global__ void essential_pick_kernel(EssState* st) {
+  if (threadIdx.x != 0) return;
+  const int* g = st->good;
+  int pick;
+  if (g[0] >= g[1] && g[0] >= g[2] && g[0] >= g[3]) pick = 0;
+  else if (g[1] >= g[0] && g[1] >= g[2] && g[1] >= g[3]) pick = 1;
+  else if (g[2] >= g[0] && g[2] >= g[1] && g[2] >= g[3]) pick = 2;
+  else pick = 3;
+  const double* R = (pick & 1) ? st->R2 : st->R1;
+  const double sg = (pick < 2) ? 1.0 : -1.0;
+  for (int k = 0; k < 9; ++k) st->R[k] = R[k];
+  for (int k = 0; k < 3; ++k) st->tt[k] = sg * st->t[k];
+  st->pick = pick;
+  st->n_good = g[pick];
+}
+
+// ---------------------------------------------------------------- Camera::projectPoints
+struct ProjCam { float K[9]; float T[12]; float umax, vmax; };
+
+__device__ __forceinline__ float dot3_rn(float a0, float b0, float a1, float b1, float a2, float b2) {
+  return __fadd_rn(__fmul_rn(a0, b0), __fadd_rn(__fmul_rn(a1, b1), __fmul_rn(a2, b2)));
+}
+
+// camera.h:24-36 in the reference's float32 evaluation order (no FMA)
+__device__ __forceinline__ bool project_point_dev(const ProjCam& c, float px, float py, float pz, float& u, float& v) {
+  const float c0 = __fadd_rn(c.T[3], dot3_rn(c.T[0], px, c.T[1], py, c.T[2], pz));
+  const float c1 = __fadd_rn(c.T[7], dot3_rn(c.T[4], px, c.T[5], py, c.T[6], pz));
+  const float c2 = __fadd_rn(c.T[11], dot3_rn(c.T[8], px, c.T[9], py, c.T[10], pz));
+  if (c2 <= 0.f) return false;
+  const float q0 = dot3_rn(c.K[0], c0, c.K[1], c1, c.K[2], c2);
+  const float q1 = dot3_rn(c.K[3], c0, c.K[4], c1, c.K[5], c2);
+  const float q2 = dot3_rn(c.K[6], c0, c.K[7], c1, c.K[8], c2);
+  const float iz = __frcp_rn(q2);
+  u = __fmul_rn(q0, iz);
+  v = __fmul_rn(q1, iz);
+  if (u < 0.f || u > c.umax) return false;
+  if (v < 0.f || v > c.vmax) return false;
+  return true;
+}
+
+__global__ void __launch_bounds__(256) project_points_kernel(ProjCam cam, const float* __restrict__ world, long long n,
+                                                             float2* __restrict__ uv, unsigned char* __restrict__ flags,
+                                                             int* __restrict__ block_counts) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  int inside = 0;
+  if (i < n) {
+    float u = -1.f, v = -1.f;
+    inside = project_point_dev(cam, __ldg(world + 3 * i), __ldg(world + 3 * i + 1), __ldg(world + 3 * i + 2), u, v);
+    uv[i] = inside ? make_float2(u, v) : make_float2(-1.f, -1.f);
+    flags[i] = (unsigned char)inside;
+  }
+  const int cnt = __syncthreads_count(inside);
+  if (threadIdx.x == 0) block_counts[blockIdx.x] = cnt;
+}
+
+__global__ void __launch_bounds__(256) compact_uv_kernel(const float2* __restrict__ uv, const unsigned char* __restrict__ flags,
+                                                         const int* __restrict__ block_offsets, long long n,
+                                                         float2* __restrict__ out) {
+  __shared__ int s_warp[8];
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  const int f = (i < n) ? flags[i] : 0;
+  const unsigned bal = __ballot_sync(0xffffffffu, f);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) s_warp[warp] = __popc(bal);
+  __syncthreads();
+  int off = block_offsets[blockIdx.x];
+  for (int w = 0; w < warp; ++w) off += s_warp[w];
+  off += __popc(bal & ((1u << lane) - 1u));
+  if (f) out[off] = uv[i];
+}
+
+// ---------------------------------------------------------------- add_new_world_points anti-join
+__global__ void __launch_bounds__(256) anti_join_kernel(const int* __restrict__ matched, long long n_matched,
+                                                        const int* __restrict__ cand, long long n_cand,
+                                                        unsigned char* __restrict__ keep, unsigned long long* n_keep) {
+  const long long j = (long long)blockIdx.x * 256 + threadIdx.x;
+  int k = 0;
+  if (j < n_cand) {
+    const int id = cand[j];
+    bool found = false;
+    for (long long i = 0; i < n_matched && !found; ++i) found = (__ldg(matched + i) == id);
+    k = !found;
+    keep[j] = (unsigned char)k;
+  }
+  const int c = __syncthreads_count(k);
+  if (threadIdx.x == 0 && c) atomicAdd(n_keep, (unsigned long long)c);
+}
+
+// P = K * T^-1[0:3,:]: float32 cv::Mat product (cv::gemm accumulates float products in double and
+// rounds to float), T^-1 from the isometry inverse (cam.cpp:108-112)
+void projection_matrix(const float K[9], const float T[12], double P[12]) {
+  float Ti[12];
+  vo_pose_inverse(T, Ti);
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 4; ++j) {
+      double s = 0;
+      for (int k = 0; k < 3; ++k) s += (double)K[3 * i + k] * (double)Ti[4 * k + j];
+      P[4 * i + j] = (double)(float)s;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int vo_triangulate_dev(vo_ctx* ctx, const float K[9], const float T1[12], const float T2[12], const float* d_x1,
+                       const float* d_x2, int64_t n, float* d_xyz_out) {
+  if (!ctx) return VO_ERR_INVALID;
+  int st = vo_ctx_activate(ctx);
+  if (st) return st;
+  VO_REQUIRE(ctx, K && T1 && T2 && n >= 0, "vo_triangulate: arguments");
+  if (n == 0) return VO_OK;  // cam.cpp:103-106: nothing to do
+  VO_REQUIRE(ctx, d_x1 && d_x2 && d_xyz_out, "vo_triangulate: null buffers");
+  ProjPair pp;
+  projection_matrix(K, T1, pp.P1);
+  projection_matrix(K, T2, pp.P2);
+  triangulate_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(
+      pp, reinterpret_cast<const float2*>(d_x1), reinterpret_cast<const float2*>(d_x2), n, d_xyz_out);
+  VO_CHECK_LAUNCH(ctx, "triangulate_kernel");
+  return VO_OK;
+}
+
+int vo_triangulate(vo_ctx* ctx, const float K[9], const float T1[12], const float T2[12], const float* x1,
+                   const float* x2, int64_t n, float* xyz_out) {
+  if (!ctx) return VO_ERR_INVALID;
+  int st = vo_ctx_activate(ctx);
+  if (st) return st;
+  VO_REQUIRE(ctx, n >= 0, "vo_triangulate: n");
+  if (n == 0) return VO_OK;
+  VO_REQUIRE(ctx, x1 && x2 && xyz_out, "vo_triangulate: null buffers");
+  char* base;
+  const size_t bx = vo_align_up((size_t)n * 8, 256);
+  st = vo_scratch(ctx, 2 * bx + (size_t)n * 12, (void**)&base);
+  if (st) return st;
+  float* dx1 = (float*)base;
+  float* dx2 = (float*)(base + bx);
+  float* dout = (float*)(base + 2 * bx);
+  VO_CUDA(ctx, cudaMemcpyAsync(dx1, x1, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  VO_CUDA(ctx, cudaMemcpyAsync(dx2, x2, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  st = vo_triangulate_dev(ctx, K, T1, T2, dx1, dx2, n, dout);
+  if (st) return st;
+  VO_CUDA(ctx, cudaMemcpyAsync(xyz_out, dout, (size_t)n * 12, cudaMemcpyDeviceToHost, ctx->stream));
+  VO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return VO_OK;
+}
+
+int vo_essential_recover(vo_ctx* ctx, const float K[9], const float* x1, const float* x2, int64_t n, double E[9],
+                         double R[9], double t[3], uint8_t* mask, int* n_good) {
+  if (!ctx) return VO_ERR_INVALID;
+  int st = vo_ctx_activate(ctx);
+  if (st) return st;
+  VO_REQUIRE(ctx, K && x1 && x2, "vo_essential_recover: null buffers");
+  VO_REQUIRE(ctx, n >= 8, "vo_essential_recover: at least 8 correspondences");
+  const EssCam cam = {(double)K[0], (double)K[4], (double)K[2], (double)K[5]};
+  long long blocks = (n + kEssThreads - 1) / kEssThreads;
+  if (blocks > ctx->sm_count) blocks = ctx->sm_count;
+  size_t off = 0;
+  auto carve = [&](size_t bytes) { size_t o = off; off = vo_align_up(off + bytes, 256); return o; };
+  const size_t o_x1 = carve((size_t)n * 8), o_x2 = carve((size_t)n * 8);
+  const size_t o_part = carve((size_t)blocks * kMom * 8), o_state = carve(sizeof(EssState));
+  const size_t o_masks = carve((size_t)n * 4);
+  char* base;
+  st = vo_scratch(ctx, off, (void**)&base);
+  if (st) return st;
+  float2* dx1 = (float2*)(base + o_x1);
+  float2* dx2 = (float2*)(base + o_x2);
+  double* part = (double*)(base + o_part);
+  EssState* dstate = (EssState*)(base + o_state);
+  unsigned char* masks = (unsigned char*)(base + o_masks);
+  VO_CUDA(ctx, cudaMemcpyAsync(dx1, x1, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  VO_CUDA(ctx, cudaMemcpyAsync(dx2, x2, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  essential_moments_kernel<<<(unsigned)blocks, kEssThreads, 0, ctx->stream>>>(cam, dx1, dx2, n, part);
+  VO_CHECK_LAUNCH(ctx, "essential_moments_kernel");
+  essential_solve_kernel<<<1, 32, 0, ctx->stream>>>(part, (int)blocks, dstate);
+  VO_CHECK_LAUNCH(ctx, "essential_solve_kernel");
+  essential_cheirality_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(cam, dx1, dx2, n, dstate, masks);
+  VO_CHECK_LAUNCH(ctx, "essential_cheirality_kernel");
+  essential_pick_kernel<<<1, 32, 0, ctx->stream>>>(dstate);
+  VO_CHECK_LAUNCH(ctx, "essential_pick_kernel");
+  void* h;
+  st = vo_pinned(ctx, sizeof(EssState), &h);
+  if (st) return st;
+  VO_CUDA(ctx, cudaMemcpyAsync(h, dstate, sizeof(EssState), cudaMemcpyDeviceToHost, ctx->stream));
+  VO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  const EssState* hs = (const EssState*)h;
+  if (E) memcpy(E, hs->E, sizeof(double) * 9);
+  if (R) memcpy(R, hs->R, sizeof(double) * 9);
+  if (t) memcpy(t, hs->tt, sizeof(double) * 3);
+  if (n_good) *n_good = hs->n_good;
+  const int pick = hs->pick;
+  if (mask) {
+    VO_CUDA(ctx, cudaMemcpyAsync(mask, masks + (size_t)pick * n, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    VO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return VO_OK;
+}
+
+int vo_project_points(vo_ctx* ctx, const float K[9], int rows, int cols, const float pose[12], const float* world_xyz,
+                      int64_t n, int keep_indices, float* out_uv, int64_t* n_out, int64_t* n_inside) {
+  if (!ctx) return VO_ERR_INVALID;
+  int st = vo_ctx_activate(ctx);
+  if (st) return st;
+  VO_REQUIRE(ctx, K && pose && n >= 0 && rows > 0 && cols > 0, "vo_project_points: arguments");
+  if (n_out) *n_out = 0;
+  if (n_inside) *n_inside = 0;
+  if (n == 0) return VO_OK;
+  VO_REQUIRE(ctx, world_xyz && out_uv, "vo_project_points: null buffers");
+  ProjCam cam;
+  for (int i = 0; i < 9; ++i) cam.K[i] = K[i];
+  for (int i = 0; i < 12; ++i) cam.T[i] = pose[i];
+  cam.umax = (float)(cols - 1);
+  cam.vmax = (float)(rows - 1);
+  const long long blocks = (n + 255) / 256;
+  size_t off = 0;
+  auto carve = [&](size_t bytes) { size_t o = off; off = vo_align_up(off + bytes, 256); return o; };
+  const size_t o_w = carve((size_t)n * 12), o_uv = carve((size_t)n * 8), o_out = carve((size_t)n * 8);
+  const size_t o_flags = carve((size_t)n), o_counts = carve((size_t)blocks * 4), o_total = carve(8);
+  char* base;
+  st = vo_scratch(ctx, off, (void**)&base);
+  if (st) return st;
+  float* dw = (float*)(base + o_w);
+  float2* duv = (float2*)(base + o_uv);
+  float2* dout = (float2*)(base + o_out);
+  unsigned char* flags = (unsigned char*)(base + o_flags);
+  int* counts = (int*)(base + o_counts);
+  long long* dtotal = (long long*)(base + o_total);
+  VO_CUDA(ctx, cudaMemcpyAsync(dw, world_xyz, (size_t)n * 12, cudaMemcpyHostToDevice, ctx->stream));
+  project_points_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(cam, dw, n, duv, flags, counts);
+  VO_CHECK_LAUNCH(ctx, "project_points_kernel");
+  st = vo_scan_block_counts(ctx, counts, blocks, dtotal);
+  if (st) return st;
+  void* h;
+  st = vo_pinned(ctx, 64, &h);
+  if (st) return st;
+  if (!keep_indices) {
+    compact_uv_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(duv, flags, counts, n, dout);
+    VO_CHECK_LAUNCH(ctx, "compact_uv_kernel");
+  }
+  VO_CUDA(ctx, cudaMemcpyAsync(h, dtotal, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  VO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  const long long inside = *(long long*)h;
+  const long long rows_out = keep_indices ? n : inside;
+  if (rows_out)
+    VO_CUDA(ctx, cudaMemcpyAsync(out_uv, keep_indices ? (void*)duv : (void*)dout, (size_t)rows_out * 8,
+                                 cudaMemcpyDeviceToHost, ctx->stream));
+  VO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (n_out) *n_out = rows_out;
+  if (n_inside) *n_inside = inside;
+  return VO_OK;
+}
+
+int vo_anti_join(vo_ctx* ctx, const int32_t* matched_id, int64_t n_matched, const int32_t* cand_id, int64_t n_cand,
+                 uint8_t* keep, int64_t* n_keep) {
+  if (!ctx) return VO_ERR_INVALID;
+  int st = vo_ctx_activate(ctx);
+  if (st) return st;
+  VO_REQUIRE(ctx, n_matched >= 0 && n_cand >= 0, "vo_anti_join: sizes");
+  if (n_keep) *n_keep = 0;
+  if (n_cand == 0) return VO_OK;
+  VO_REQUIRE(ctx, cand_id && keep && (n_matched == 0 || matched_id), "vo_anti_join: null buffers");
+  size_t off = 0;
+  auto carve = [&](size_t bytes) { size_t o = off; off = vo_align_up(off + bytes, 256); return o; };
+  const size_t o_m = carve((size_t)(n_matched ? n_matched : 1) * 4), o_c = carve((size_t)n_cand * 4);
+  const size_t o_k = carve((size_t)n_cand), o_n = carve(8);
+  char* base;
+  st = vo_scratch(ctx, off, (void**)&base);
+  if (st) return st;
+  int* dm = (int*)(base + o_m);
+  int* dc = (int*)(base + o_c);
+  unsigned char* dk = (unsigned char*)(base + o_k);
+  unsigned long long* dn = (unsigned long long*)(base + o_n);
+  if (n_matched) VO_CUDA(ctx, cudaMemcpyAsync(dm, matched_id, (size_t)n_matched * 4, cudaMemcpyHostToDevice, ctx->stream));
+  VO_CUDA(ctx, cudaMemcpyAsync(dc, cand_id, (size_t)n_cand * 4, cudaMemcpyHostToDevice, ctx->stream));
+  VO_CUDA(ctx, cudaMemsetAsync(dn, 0, 8, ctx->stream));
+  anti_join_kernel<<<(unsigned)((n_cand + 255) / 256), 256, 0, ctx->stream>>>(dm, n_matched, dc, n_cand, dk, dn);
+  VO_CHECK_LAUNCH(ctx, "anti_join_kernel");
+  void* h;
+  st = vo_pinned(ctx, 64, &h);
+  if (st) return st;
+  VO_CUDA(ctx, cudaMemcpyAsync(keep, dk, (size_t)n_cand, cudaMemcpyDeviceToHost, ctx->stream));
+  VO_CUDA(ctx, cudaMemcpyAsync(h, dn, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  VO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (n_keep) *n_keep = (int64_t) * (unsigned long long*)h;
+  return VO_OK;
+}
+
+}  // extern "C"

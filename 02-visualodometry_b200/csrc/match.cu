@@ -1,0 +1,469 @@
+// match.cu — brute-force descriptor matching on sm_100a.
+//
+// Replaces the header template match_points<P1,P2> (reference src/my_utilities.h:70-120):
+// for every query row i, best / second-best squared L2 distance over all rows j of the other
+// set, lowest index on ties, accepted iff best < 0.2 && best/second < 0.8.
+//
+// Layout: descriptors packed row-major float[N][D] (the shim gathers them out of the
+// reference's per-record heap VectorXf).  Work decomposition:
+//   grid.x = query-row blocks (one row per thread: its D floats live in registers)
+//   grid.y = column splits of the other set, sized so the grid fills whole waves of SMs
+//   each CTA streams its column range through shared memory in tiles (rows padded to a
+//   multiple of 4 floats -> conflict-free broadcast LDS.128)
+// followed by an exact merge of the per-split (best, second, idx) triples in split order, the
+// threshold/ratio test and a stable (ascending i) compaction.
+//
+// Rounding contract: the distance is evaluated in float32 with explicit round-to-nearest
+// sub/mul/add in the order Eigen's SSE squaredNorm redux uses for VectorXf;
+// nothing is contracted to FMA, so indices and accept flags are bit-exact against the oracle.
+// This is FP32-issue bound (30 flop per pair, D = 10): no tensor cores, see DESIGN.md.
+#include "vo_common.cuh"
+
+#include <float.h>
+
+namespace {
+
+constexpr int kMatchThreads = 128;
+constexpr int kTileRows = 256;  // rows of B per shared-memory tile
+constexpr int kMaxDim = 16;
+
+template <int DIM>
+__device__ __forceinline__ float sq_term(const float (&a)[DIM], const float* __restrict__ b, int k) {
+  const float d = __fsub_rn(a[k], b[k]);
+  return __fmul_rn(d, d);
+}
+
+// (a-b).squaredNorm() in Eigen's LinearVectorizedTraversal order with 4-wide packets
+template <int DIM>
+__device__ __forceinline__ float sqdist_eigen(const float (&a)[DIM], const float* __restrict__ b) {
+  if (DIM < 4) {
+    float r = sq_term<DIM>(a, b, 0);
+#pragma unroll
+    for (int k = 1; k < DIM; ++k) r = __fadd_rn(r, sq_term<DIM>(a, b, k));
+    return r;
+  }
+  constexpr int n4 = DIM / 4 * 4, n8 = DIM / 8 * 8;
+  float p0[4], p1[4];
+#pragma unroll
+  for (int l = 0; l < 4; ++l) p0[l] = sq_term<DIM>(a, b, l);
+  if (n4 > 4) {
+#pragma unroll
+    for (int l = 0; l < 4; ++l) p1[l] = sq_term<DIM>(a, b, 4 + l);
+#pragma unroll
+    for (int i = 8; i < n8; i += 8)
+#pragma unroll
+      for (int l = 0; l < 4; ++l) {
+        p0[l] = __fadd_rn(p0[l], sq_term<DIM>(a, b, i + l));
+        p1[l] = __fadd_rn(p1[l], sq_term<DIM>(a, b, i + 4 + l));
+      }
+#pragma unroll
+    for (int l = 0; l < 4; ++l) p0[l] = __fadd_rn(p0[l], p1[l]);
+    if (n4 > n8) {
+#pragma unroll
+      for (int l = 0; l < 4; ++l) p0[l] = __fadd_rn(p0[l], sq_term<DIM>(a, b, n8 + l));
+    }
+  }
+  float r = __fadd_rn(__fadd_rn(p0[0], p0[2]), __fadd_rn(p0[1], p0[3]));
+#pragma unroll
+  for (int k = n4; k < DIM; ++k) r = __fadd_rn(r, sq_term<DIM>(a, b, k));
+  return r;
+}
+
+// my_utilities.h:93-99
+__device__ __forceinline__ void update_best(float d, int j, float& best, float& second, int& idx) {
+  const bool lt = d < best;
+  const float s2 = (d < second) ? d : second;
+  second = lt ? best : s2;
+  idx = lt ? j : idx;
+  best = lt ? d : best;
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(kMatchThreads) match_scan_kernel(
+    const float* __restrict__ A, long long row_begin, long long row_end, const float* __restrict__ B,
+    long long n2, long long split_size, float* __restrict__ o_best, float* __restrict__ o_second,
+    int* __restrict__ o_idx) {
+  constexpr int DP = (DIM + 3) / 4 * 4;
+  __shared__ __align__(16) float sB[kTileRows * DP];
+  const long long rows = row_end - row_begin;
+  const long long r = (long long)blockIdx.x * kMatchThreads + threadIdx.x;
+  const bool valid = r < rows;
+  float a[DIM];
+#pragma unroll
+  for (int k = 0; k < DIM; ++k) a[k] = valid ? __ldg(A + (row_begin + r) * DIM + k) : 0.f;
+  float best = FLT_MAX, second = FLT_MAX;
+  int idx = -1;
+  const long long j_lo = (long long)blockIdx.y * split_size;
+  const long long j_hi = (j_lo + split_size < n2) ? j_lo + split_size : n2;
+  for (long long j0 = j_lo; j0 < j_hi; j0 += kTileRows) {
+    const int cnt = (int)((j_hi - j0 < kTileRows) ? (j_hi - j0) : kTileRows);
+    __syncthreads();
+    for (int t = threadIdx.x; t < cnt * DIM; t += kMatchThreads) {
+      const int jj = t / DIM, k = t - jj * DIM;
+      sB[jj * DP + k] = __ldg(B + j0 * DIM + t);
+    }
+    __syncthreads();
+    int jj = 0;
+    for (; jj + 4 <= cnt; jj += 4) {
+      const float d0 = sqdist_eigen<DIM>(a, sB + (jj + 0) * DP);
+      const float d1 = sqdist_eigen<DIM>(a, sB + (jj + 1) * DP);
+      const float d2 = sqdist_eigen<DIM>(a, sB + (jj + 2) * DP);
+      const float d3 = sqdist_eigen<DIM>(a, sB + (jj + 3) * DP);
+      const int j = (int)(j0 + jj);
+      update_best(d0, j, best, second, idx);
+      update_best(d1, j + 1, best, second, idx);
+      update_best(d2, j + 2, best, second, idx);
+      update_best(d3, j + 3, best, second, idx);
+    }
+    for (; jj < cnt; ++jj) update_best(sqdist_eigen<DIM>(a, sB + jj * DP), (int)(j0 + jj), best, second, idx);
+  }
+  if (valid) {
+    const long long o = (long long)blockIdx.y * rows + r;
+    o_best[o] = best;
+    o_second[o] = second;
+    o_idx[o] = idx;
+  }
+}
+
+// merge the per-split triples in ascending split order (exact: comparisons only), apply the
+// accept test (my_utilities.h:103-105) and count accepted rows per block of 256.
+__global__ void __launch_bounds__(256) match_merge_kernel(
+    const float* __restrict__ p_best, const float* __restrict__ p_second, const int* __restrict__ p_idx,
+    long long rows, int n_splits, float dist_thr, float ratio_thr, float* __restrict__ o_best,
+    float* __restrict__ o_second, int* __restrict__ o_idx, unsigned char* __restrict__ flags,
+    int* __restrict__ block_counts) {
+  const long long r = (long long)blockIdx.x * 256 + threadIdx.x;
+  int acc = 0;
+  if (r < rows) {
+    float best = FLT_MAX, second = FLT_MAX;
+    int idx = -1;
+    for (int s = 0; s < n_splits; ++s) {
+      const float b = p_best[(long long)s * rows + r], s2 = p_second[(long long)s * rows + r];
+      const int i = p_idx[(long long)s * rows + r];
+      if (i < 0) continue;  // empty split or no distance below FLT_MAX
+      // replay "b then s2" through the sequential rule: b carries the index, s2 only a value
+      update_best(b, i, best, second, idx);
+      if (s2 < second) second = s2;
+    }
+    acc = (idx != -1) && (best < dist_thr) && (__fdiv_rn(best, second) < ratio_thr);
+    if (o_best) o_best[r] = best;
+    if (o_second) o_second[r] = second;
+    o_idx[r] = idx;
+    flags[r] = (unsigned char)acc;
+  }
+  const int cnt = __syncthreads_count(acc);
+  if (threadIdx.x == 0) block_counts[blockIdx.x] = cnt;
+}
+
+// exclusive scan of the per-block counts by one CTA (fixed order -> deterministic offsets)
+__global__ void __launch_bounds__(1024) match_scan_counts_kernel(int* __restrict__ counts, long long n_blocks,
+                                                                 long long* __restrict__ total) {
+  __shared__ long long s_warp[32];
+  __shared__ long long s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (long long base = 0; base < n_blocks; base += 1024) {
+    const long long i = base + threadIdx.x;
+    const int v = (i < n_blocks) ? counts[i] : 0;
+    long long x = v;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const long long y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) s_warp[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      long long w = s_warp[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const long long y = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += y;
+      }
+      s_warp[lane] = w;
+    }
+    __syncthreads();
+    const long long incl = x + (warp ? s_warp[warp - 1] : 0) + s_carry;
+    if (i < n_blocks) counts[i] = (int)(incl - v);  // exclusive offset (fits: <= rows < 2^31 per call)
+    __syncthreads();
+    if (threadIdx.x == 1023) s_carry = incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = s_carry;
+}
+
+__global__ void __launch_bounds__(256) match_scatter_kernel(
+    const unsigned char* __restrict__ flags, const int* __restrict__ idx, const int* __restrict__ block_offsets,
+    long long rows, long long row_begin, long long capacity, const int* __restrict__ idA,
+    const int* __restrict__ idB, int2* __restrict__ pairs, unsigned long long* __restrict__ correct) {
+  __shared__ int s_warp[8];
+  const long long r = (long long)blockIdx.x * 256 + threadIdx.x;
+  const int f = (r < rows) ? flags[r] : 0;
+  const unsigned bal = __ballot_sync(0xffffffffu, f);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) s_warp[warp] = __popc(bal);
+  __syncthreads();
+  int off = block_offsets[blockIdx.x];
+  for (int w = 0; w < warp; ++w) off += s_warp[w];
+  off += __popc(bal & ((1u << lane) - 1u));
+  int ok = 0;
+  if (f) {
+    const int j = idx[r];
+    if (off < capacity) pairs[off] = make_int2((int)(row_begin + r), j);
+    if (idA && idB) ok = (idA[row_begin + r] == idB[j]);
+  }
+  const int c = __syncthreads_count(ok);
+  if (threadIdx.x == 0 && c) atomicAdd(correct, (unsigned long long)c);
+}
+
+// ---- id_real join for the printed statistics (my_utilities.h:89-91): the reference counts
+// equal-id pairs inside the O(N1*N2) loop; the same integer comes out of a hash join.
+constexpr unsigned long long kEmptySlot = 0xFFFFFFFFFFFFFFFFull;
+
+__device__ __forceinline__ unsigned hash_u32(unsigned x) {
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  return x;
+}
+
+__global__ void idjoin_build_kernel(const int* __restrict__ idB, long long n2, unsigned long long* table,
+                                    unsigned mask) {
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n2) return;
+  const unsigned key = (unsigned)idB[j];
+  unsigned h = hash_u32(key) & mask;
+  while (true) {
+    unsigned long long cur = table[h];
+    if (cur == kEmptySlot) {
+      const unsigned long long want = (1ull << 32) | key;
+      const unsigned long long old = atomicCAS(&table[h], kEmptySlot, want);
+      if (old == kEmptySlot) return;
+      cur = old;
+    }
+    if ((unsigned)(cur & 0xFFFFFFFFull) == key) {
+      atomicAdd(&table[h], 1ull << 32);
+      return;
+    }
+    h = (h + 1) & mask;
+  }
+}
+
+__global__ void idjoin_probe_kernel(const int* __restrict__ idA, long long row_begin, long long row_end,
+                                    const unsigned long long* __restrict__ table, unsigned mask,
+                                    unsigned long long* possible) {
+  const long long i = row_begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long c = 0;
+  if (i < row_end) {
+    const unsigned key = (unsigned)idA[i];
+    unsigned h = hash_u32(key) & mask;
+    while (true) {
+      const unsigned long long cur = table[h];
+      if (cur == kEmptySlot) break;
+      if ((unsigned)(cur & 0xFFFFFFFFull) == key) {
+        c = cur >> 32;
+        break;
+      }
+      h = (h + 1) & mask;
+    }
+  }
+  // integer sum: order-independent, so atomics stay deterministic
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(possible, c);
+}
+
+template <int DIM>
+void launch_scan(dim3 grid, cudaStream_t st, const float* A, long long rb, long long re, const float* B,
+                 long long n2, long long split, float* ob, float* os, int* oi) {
+  match_scan_kernel<DIM><<<grid, kMatchThreads, 0, st>>>(A, rb, re, B, n2, split, ob, os, oi);
+}
+
+typedef void (*scan_fn)(dim3, cudaStream_t, const float*, long long, long long, const float*, long long, long long,
+                        float*, float*, int*);
+
+scan_fn scan_for_dim(int dim) {
+  switch (dim) {
+    case 1: return launch_scan<1>;   case 2: return launch_scan<2>;   case 3: return launch_scan<3>;
+    case 4: return launch_scan<4>;   case 5: return launch_scan<5>;   case 6: return launch_scan<6>;
+    case 7: return launch_scan<7>;   case 8: return launch_scan<8>;   case 9: return launch_scan<9>;
+    case 10: return launch_scan<10>; case 11: return launch_scan<11>; case 12: return launch_scan<12>;
+    case 13: return launch_scan<13>; case 14: return launch_scan<14>; case 15: return launch_scan<15>;
+    case 16: return launch_scan<16>;
+    default: return nullptr;
+  }
+}
+
+}  // namespace
+
+int vo_scan_block_counts(vo_ctx* ctx, int* d_counts, long long n_blocks, long long* d_total) {
+  match_scan_counts_kernel<<<1, 1024, 0, ctx->stream>>>(d_counts, n_blocks, d_total);
+  VO_CHECK_LAUNCH(ctx, "match_scan_counts_kernel");
+  return VO_OK;
+}
+
+extern "C" {
+
+int vo_match_dev(vo_ctx* ctx, const float* d_descA, int64_t n1, const float* d_descB, int64_t n2, int dim,
+                 float dist_thr, float ratio_thr, const int32_t* d_idA, const int32_t* d_idB, int64_t row_begin,
+                 int64_t row_end, int32_t* d_pairs_out, int64_t capacity, int64_t* n_out, int64_t stats[2],
+                 float* d_best, float* d_second, int32_t* d_best_idx) {
+  if (!ctx) return VO_ERR_INVALID;
+  int st = vo_ctx_activate(ctx);
+  if (st) return st;
+  VO_REQUIRE(ctx, n1 >= 0 && n2 >= 0 && n2 < 0x7fffffffLL, "vo_match: sizes");
+  VO_REQUIRE(ctx, dim >= 1 && dim <= kMaxDim, "vo_match: descriptor dimension must be in [1,16]");
+  VO_REQUIRE(ctx, row_begin >= 0 && row_begin <= row_end && row_end <= n1, "vo_match: row range");
+  VO_REQUIRE(ctx, n_out != nullptr && capacity >= 0, "vo_match: outputs");
+  const long long rows = row_end - row_begin;
+  *n_out = 0;
+  if (stats) stats[0] = stats[1] = 0;
+  if (rows == 0) return VO_OK;
+  VO_REQUIRE(ctx, rows < 0x7fffffffLL, "vo_match: at most 2^31-1 rows per call");
+  VO_REQUIRE(ctx, d_descA && (n2 == 0 || d_descB), "vo_match: null descriptors");
+  VO_REQUIRE(ctx, capacity == 0 || d_pairs_out, "vo_match: null pairs_out");
+
+  // column splits: fill whole waves (sm_count * resident CTAs) without starving any CTA of work
+  const long long row_blocks = (rows + kMatchThreads - 1) / kMatchThreads;
+  const long long slots = (long long)ctx->sm_count * 8;
+  long long n_splits = 1;
+  if (row_blocks < 2 * slots && n2 > 0) {
+    n_splits = (2 * slots + row_blocks - 1) / row_blocks;
+    const long long max_splits = (n2 + 4 * kTileRows - 1) / (4 * kTileRows);
+    if (n_splits > max_splits) n_splits = max_splits;
+    if (n_splits < 1) n_splits = 1;
+    if (n_splits > 65535) n_splits = 65535;
+  }
+  long long split_size = n2 > 0 ? (n2 + n_splits - 1) / n_splits : 1;
+  split_size = (split_size + kTileRows - 1) / kTileRows * kTileRows;
+  n_splits = n2 > 0 ? (n2 + split_size - 1) / split_size : 1;
+
+  const long long merge_blocks = (rows + 255) / 256;
+  const bool want_ids = d_idA && d_idB;
+  unsigned table_size = 0;
+  if (want_ids && n2 > 0) {
+    table_size = 64;
+    while ((long long)table_size < 2 * n2) table_size <<= 1;
+  }
+  // scratch carve-up
+  size_t off = 0;
+  auto carve = [&](size_t bytes) { size_t o = off; off = vo_align_up(off + bytes, 256); return o; };
+  const size_t o_pb = carve((size_t)n_splits * rows * 4), o_ps = carve((size_t)n_splits * rows * 4);
+  const size_t o_pi = carve((size_t)n_splits * rows * 4), o_idx = carve((size_t)rows * 4);
+  const size_t o_flags = carve((size_t)rows), o_counts = carve((size_t)merge_blocks * 4);
+  const size_t o_small = carve(64), o_table = carve((size_t)table_size * 8);
+  char* base;
+  st = vo_scratch(ctx, off, (void**)&base);
+  if (st) return st;
+  float* pb = (float*)(base + o_pb);
+  float* ps = (float*)(base + o_ps);
+  int* pi = (int*)(base + o_pi);
+  int* idx = d_best_idx ? d_best_idx : (int*)(base + o_idx);
+  unsigned char* flags = (unsigned char*)(base + o_flags);
+  int* counts = (int*)(base + o_counts);
+  long long* d_total = (long long*)(base + o_small);
+  unsigned long long* d_correct = (unsigned long long*)(base + o_small + 8);
+  unsigned long long* d_possible = (unsigned long long*)(base + o_small + 16);
+  unsigned long long* table = (unsigned long long*)(base + o_table);
+  VO_CUDA(ctx, cudaMemsetAsync(d_total, 0, 64, ctx->stream));
+
+  scan_fn scan = scan_for_dim(dim);
+  dim3 grid((unsigned)row_blocks, (unsigned)n_splits);
+  scan(grid, ctx->stream, d_descA, row_begin, row_end, d_descB, n2, split_size, pb, ps, pi);
+  VO_CHECK_LAUNCH(ctx, "match_scan_kernel");
+  match_merge_kernel<<<(unsigned)merge_blocks, 256, 0, ctx->stream>>>(pb, ps, pi, rows, (int)n_splits, dist_thr,
+                                                                      ratio_thr, d_best, d_second, idx, flags,
+                                                                      counts);
+  VO_CHECK_LAUNCH(ctx, "match_merge_kernel");
+  st = vo_scan_block_counts(ctx, counts, merge_blocks, d_total);
+  if (st) return st;
+  match_scatter_kernel<<<(unsigned)merge_blocks, 256, 0, ctx->stream>>>(
+      flags, idx, counts, rows, row_begin, capacity, want_ids ? d_idA : nullptr, want_ids ? d_idB : nullptr,
+      reinterpret_cast<int2*>(d_pairs_out), d_correct);
+  VO_CHECK_LAUNCH(ctx, "match_scatter_kernel");
+  if (want_ids && n2 > 0) {
+    VO_CUDA(ctx, cudaMemsetAsync(table, 0xFF, (size_t)table_size * 8, ctx->stream));
+    idjoin_build_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, ctx->stream>>>(d_idB, n2, table, table_size - 1);
+    VO_CHECK_LAUNCH(ctx, "idjoin_build_kernel");
+    idjoin_probe_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, ctx->stream>>>(d_idA, row_begin, row_end, table,
+                                                                               table_size - 1, d_possible);
+    VO_CHECK_LAUNCH(ctx, "idjoin_probe_kernel");
+  }
+  void* h;
+  st = vo_pinned(ctx, 64, &h);
+  if (st) return st;
+  VO_CUDA(ctx, cudaMemcpyAsync(h, d_total, 24, cudaMemcpyDeviceToHost, ctx->stream));
+  VO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  const long long total = ((long long*)h)[0];
+  *n_out = total;
+  if (stats) {
+    stats[1] = (int64_t)((unsigned long long*)h)[1];
+    stats[0] = (int64_t)((unsigned long long*)h)[2];
+  }
+  if (total > capacity) return vo_set_error(ctx, VO_ERR_CAPACITY, "vo_match", "pairs_out capacity");
+  return VO_OK;
+}
+
+int vo_match(vo_ctx* ctx, const float* descA, int64_t n1, const float* descB, int64_t n2, int dim, float dist_thr,
+             float ratio_thr, const int32_t* idA, const int32_t* idB, int64_t row_begin, int64_t row_end,
+             int32_t* pairs_out, int64_t capacity, int64_t* n_out, int64_t stats[2]) {
+  if (!ctx) return VO_ERR_INVALID;
+  int st = vo_ctx_activate(ctx);
+  if (st) return st;
+  VO_REQUIRE(ctx, n1 >= 0 && n2 >= 0 && dim >= 1 && dim <= kMaxDim, "vo_match: sizes");
+  VO_REQUIRE(ctx, row_begin >= 0 && row_begin <= row_end && row_end <= n1, "vo_match: row range");
+  VO_REQUIRE(ctx, n_out != nullptr, "vo_match: n_out");
+  const long long rows = row_end - row_begin;
+  *n_out = 0;
+  if (stats) stats[0] = stats[1] = 0;
+  if (rows == 0) return VO_OK;
+  VO_REQUIRE(ctx, descA && (n2 == 0 || descB), "vo_match: null descriptors");
+  const bool ids = idA && idB;
+  // host staging: only the row range of A travels
+  const size_t bA = (size_t)rows * dim * 4, bB = (size_t)n2 * dim * 4;
+  const size_t bIA = ids ? (size_t)rows * 4 : 0, bIB = ids ? (size_t)n2 * 4 : 0, bP = (size_t)rows * 8;
+  float *dA = nullptr, *dB = nullptr;
+  int32_t *dIA = nullptr, *dIB = nullptr, *dP = nullptr;
+  cudaError_t e = cudaMalloc((void**)&dA, bA ? bA : 4);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&dB, bB ? bB : 4);
+  if (e == cudaSuccess && ids) e = cudaMalloc((void**)&dIA, bIA ? bIA : 4);
+  if (e == cudaSuccess && ids) e = cudaMalloc((void**)&dIB, bIB ? bIB : 4);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&dP, bP);
+  auto cleanup = [&]() {
+    if (dA) cudaFree(dA);
+    if (dB) cudaFree(dB);
+    if (dIA) cudaFree(dIA);
+    if (dIB) cudaFree(dIB);
+    if (dP) cudaFree(dP);
+  };
+  if (e != cudaSuccess) {
+    cleanup();
+    return vo_set_error(ctx, VO_ERR_NOMEM, "vo_match: cudaMalloc", cudaGetErrorString(e));
+  }
+  e = cudaMemcpyAsync(dA, descA + row_begin * dim, bA, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess && bB) e = cudaMemcpyAsync(dB, descB, bB, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess && ids) e = cudaMemcpyAsync(dIA, idA + row_begin, bIA, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess && ids && bIB) e = cudaMemcpyAsync(dIB, idB, bIB, cudaMemcpyHostToDevice, ctx->stream);
+  if (e != cudaSuccess) {
+    cleanup();
+    return vo_set_error(ctx, VO_ERR_CUDA, "vo_match: H2D", cudaGetErrorString(e));
+  }
+  int64_t n = 0;
+  st = vo_match_dev(ctx, dA, rows, dB, n2, dim, dist_thr, ratio_thr, dIA, dIB, 0, rows, dP, rows, &n, stats, nullptr,
+                    nullptr, nullptr);
+  if (st == VO_OK) {
+    *n_out = n;
+    if (n > capacity) {
+      st = vo_set_error(ctx, VO_ERR_CAPACITY, "vo_match", "pairs_out capacity");
+    } else if (n) {
+      e = cudaMemcpyAsync(pairs_out, dP, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+      if (e != cudaSuccess) st = vo_set_error(ctx, VO_ERR_CUDA, "vo_match: D2H", cudaGetErrorString(e));
+      for (int64_t k = 0; k < n; ++k) pairs_out[2 * k] += (int32_t)row_begin;  // back to global row ids
+    }
+  }
+  cudaStreamSynchronize(ctx->stream);
+  cleanup();
+  return st;
+}
+
+}  // extern "C"

@@ -1,0 +1,84 @@
+// vo_common.cuh — context, error plumbing and small device helpers shared by the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <new>
+#include <string.h>
+
+#include "../../include/vo_b200.h"
+
+struct vo_nccl;  // resolved at run time, see comm.cu
+
+struct vo_ctx {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int64_t launches = 0;
+  char err[256] = {0};
+  // scratch arena (device) reused by the stateless entry points; grows monotonically
+  void* scratch = nullptr;
+  size_t scratch_bytes = 0;
+  // pinned host staging for small synchronous read-backs
+  void* pinned = nullptr;
+  size_t pinned_bytes = 0;
+  // communicator (nullptr on a single GPU)
+  void* nccl_comm = nullptr;
+  int n_ranks = 1;
+  int rank = 0;
+};
+
+int vo_set_error(vo_ctx* ctx, int status, const char* what, const char* detail);
+
+#define VO_CUDA(ctx, call)                                                              \
+  do {                                                                                  \
+    cudaError_t e__ = (call);                                                           \
+    if (e__ != cudaSuccess) return vo_set_error((ctx), VO_ERR_CUDA, #call, cudaGetErrorString(e__)); \
+  } while (0)
+
+#define VO_CHECK_LAUNCH(ctx, name)                                                      \
+  do {                                                                                  \
+    (ctx)->launches++;                                                                  \
+    cudaError_t e__ = cudaGetLastError();                                               \
+    if (e__ != cudaSuccess) return vo_set_error((ctx), VO_ERR_CUDA, name, cudaGetErrorString(e__)); \
+  } while (0)
+
+#define VO_REQUIRE(ctx, cond, msg)                                         \
+  do {                                                                     \
+    if (!(cond)) return vo_set_error((ctx), VO_ERR_INVALID, msg, #cond);   \
+  } while (0)
+
+// device scratch of at least `bytes` (256-B aligned), valid until the next vo_scratch call
+int vo_scratch(vo_ctx* ctx, size_t bytes, void** out);
+int vo_pinned(vo_ctx* ctx, size_t bytes, void** out);
+int vo_ctx_activate(vo_ctx* ctx);
+
+// all-reduce (sum) of n doubles in place on the context stream; no-op without a communicator
+int vo_comm_allreduce_f64(vo_ctx* ctx, double* d_buf, int n);
+
+// in-place exclusive scan of per-block counts by one CTA (fixed order); *d_total = grand total
+int vo_scan_block_counts(vo_ctx* ctx, int* d_counts, long long n_blocks, long long* d_total);
+
+static inline size_t vo_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+#ifdef __CUDACC__
+// streaming 128-bit load: read-only path, do not allocate in L1 (data is touched once per launch)
+__device__ __forceinline__ float4 ldg_stream4(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ int warp_sum_i(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+#endif

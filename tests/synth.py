@@ -1,0 +1,82 @@
+"""Seeded synthetic workloads of the shapes BASELINE.json names.
+Shared by the tests, __graft_entry__.smoke() and bench.py. numpy only."""
+import numpy as np
+
+K_REF = np.array([[180, 0, 320], [0, 180, 240], [0, 0, 1]], np.float32)
+ROWS, COLS = 480, 640
+
+
+def euler_pose(dx):
+    """v2tEuler (reference src/defs.h:131-136) in float64 -> 3x4."""
+    a, b, c = dx[3:6]
+    Rx = np.array([[1, 0, 0], [0, np.cos(a), -np.sin(a)], [0, np.sin(a), np.cos(a)]])
+    Ry = np.array([[np.cos(b), 0, np.sin(b)], [0, 1, 0], [-np.sin(b), 0, np.cos(b)]])
+    Rz = np.array([[np.cos(c), -np.sin(c), 0], [np.sin(c), np.cos(c), 0], [0, 0, 1]])
+    T = np.zeros((3, 4))
+    T[:, :3] = Rx @ Ry @ Rz
+    T[:, 3] = dx[:3]
+    return T
+
+
+def picp_frame(n=1 << 20, seed=42, permute=False, outlier_frac=0.10, invalid_frac=0.02, noise_px=0.5,
+               n_world=None):
+    """One PICP frame (config 2/3): world points generated in the GT camera frame
+    (u~U(0,639), v~U(0,479), z~U(0.5,5)), back-projected, moved to the world by a GT pose;
+    measurements = projection + N(0,noise_px); `outlier_frac` gross outliers (uniform pixel);
+    `invalid_frac` points behind the camera; initial pose = perturbation o GT (|dt|=0.05, 0.02 rad
+    per axis). Correspondences: identity (variant A) or a random permutation (variant B)."""
+    rng = np.random.Generator(np.random.Philox(seed))
+    n_world = n if n_world is None else n_world
+    Kd = K_REF.astype(np.float64)
+    u = rng.uniform(0, 639, n_world)
+    v = rng.uniform(0, 479, n_world)
+    z = rng.uniform(0.5, 5.0, n_world)
+    cam = np.stack([(u - Kd[0, 2]) / Kd[0, 0] * z, (v - Kd[1, 2]) / Kd[1, 1] * z, z], 1)
+    bad = rng.random(n_world) < invalid_frac
+    cam[bad, 2] *= -1.0  # behind the camera
+    gt = euler_pose(np.array([0.3, -0.2, 0.5, 0.05, -0.03, 0.08]))  # world-in-camera GT
+    Rg, tg = gt[:, :3], gt[:, 3]
+    world = (cam - tg) @ Rg  # R^T (c - t)
+    meas = np.stack([u, v], 1) + rng.normal(0, noise_px, (n_world, 2))
+    out = rng.random(n_world) < outlier_frac
+    meas[out] = np.stack([rng.uniform(0, 639, out.sum()), rng.uniform(0, 479, out.sum())], 1)
+    d = rng.normal(size=3)
+    d *= 0.05 / np.linalg.norm(d)
+    pert = euler_pose(np.array([d[0], d[1], d[2], 0.02, -0.02, 0.02]))
+    pose0 = np.zeros((3, 4))
+    pose0[:, :3] = pert[:, :3] @ Rg
+    pose0[:, 3] = pert[:, :3] @ tg + pert[:, 3]
+    if permute:
+        perm = rng.permutation(n_world).astype(np.int32)[:n]
+        # image points stay in order (first ascending), world indices are scattered (second arbitrary)
+        world_p = np.empty_like(world)
+        world_p[perm] = world[:n] if n == n_world else world[perm]
+        if n == n_world:
+            world = world_p
+            pairs = np.stack([np.arange(n, dtype=np.int32), perm], 1)
+        else:
+            pairs = np.stack([perm, perm], 1)
+    else:
+        pairs = np.stack([np.arange(n, dtype=np.int32), np.arange(n, dtype=np.int32)], 1)
+    return dict(K=K_REF.copy(), rows=ROWS, cols=COLS, world=world.astype(np.float32),
+                image=meas.astype(np.float32), pairs=np.ascontiguousarray(pairs, np.int32),
+                pose0=pose0.astype(np.float32), pose_gt=gt.astype(np.float32))
+
+
+def descriptors(n1, n2, dim=10, seed=42, copy_frac=0.9, dup_frac=0.001, noise=0.0):
+    """Config 4: descB ~ U(-1,1)^dim with `dup_frac` exact duplicate rows; descA: `copy_frac` exact
+    copies of random rows of descB (+ optional N(0,noise)), the rest fresh U(-1,1)^dim."""
+    rng = np.random.Generator(np.random.Philox(seed))
+    B = rng.uniform(-1, 1, (n2, dim)).astype(np.float32)
+    ndup = int(n2 * dup_frac)
+    if ndup and n2 > 1:
+        src = rng.integers(0, n2, ndup)
+        dst = rng.integers(0, n2, ndup)
+        B[dst] = B[src]
+    A = rng.uniform(-1, 1, (n1, dim)).astype(np.float32)
+    if n2 > 0:
+        cp = rng.random(n1) < copy_frac
+        A[cp] = B[rng.integers(0, n2, int(cp.sum()))]
+    if noise > 0:
+        A = (A + rng.normal(0, noise, A.shape)).astype(np.float32)
+    return np.ascontiguousarray(A), np.ascontiguousarray(B)

@@ -1,0 +1,139 @@
+"""GPU parity tests for brute-force descriptor matching: indices, accept flags and the per-row
+best / second-best distances are BIT-EXACT against the oracle (same float32 evaluation order)."""
+import numpy as np
+import pytest
+
+import replay
+import synth
+from backends import product
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    vo = product()
+    c = vo.Context(0)
+    yield c
+    c.close()
+
+
+def _rows_dev(ctx, A, B, row_begin=0, row_end=None):
+    import torch
+    n1, dim = A.shape
+    row_end = n1 if row_end is None else row_end
+    rows = row_end - row_begin
+    dA, dB = torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda()
+    best = torch.empty(max(rows, 1), dtype=torch.float32, device="cuda")
+    second = torch.empty_like(best)
+    idx = torch.empty(max(rows, 1), dtype=torch.int32, device="cuda")
+    pairs = torch.empty((max(rows, 1), 2), dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    n, stats = ctx.match_dev(dA.data_ptr(), n1, dB.data_ptr(), len(B), dim, pairs.data_ptr(), rows, row_begin=row_begin,
+                             row_end=row_end, d_best=best.data_ptr(), d_second=second.data_ptr(), d_idx=idx.data_ptr())
+    torch.cuda.synchronize()
+    return pairs[:n].cpu().numpy(), best[:rows].cpu().numpy(), second[:rows].cpu().numpy(), idx[:rows].cpu().numpy()
+
+
+@pytest.mark.parametrize("n1,n2,dim", [(1, 1, 10), (1, 2, 10), (7, 3, 10), (127, 490, 10), (300, 1000, 10),
+                                       (2049, 777, 10), (513, 4099, 10), (64, 64, 3), (100, 200, 4), (100, 200, 7),
+                                       (100, 200, 8), (100, 200, 12), (100, 200, 16)])
+def test_match_bit_exact(ctx, oracle, n1, n2, dim):
+    A, B = synth.descriptors(n1, n2, dim=dim, seed=n1 * 31 + n2, dup_frac=0.02)
+    idA = np.arange(n1, dtype=np.int32) % 50
+    idB = np.arange(n2, dtype=np.int32) % 50
+    pairs, stats = ctx.match(A, B, 0.2, 0.8, idA, idB)
+    rp, rstats, rbest, rsecond, ridx = oracle.match(A, B, 0.2, 0.8, idA, idB, want_rows=True)
+    assert np.array_equal(pairs, rp)
+    assert stats == rstats
+    p2, best, second, idx = _rows_dev(ctx, A, B)
+    assert np.array_equal(p2, rp)
+    assert np.array_equal(idx, ridx)
+    assert np.array_equal(best.view(np.uint32), rbest.view(np.uint32))
+    assert np.array_equal(second.view(np.uint32), rsecond.view(np.uint32))
+
+
+def test_match_noisy_and_threshold_edge(ctx, oracle):
+    """noise puts many best distances near 0.2 and ratios near 0.8: exact rounding decides"""
+    A, B = synth.descriptors(4000, 6000, seed=9, copy_frac=0.7, noise=0.14)
+    pairs, _ = ctx.match(A, B)
+    rp, _, rbest, rsecond, _ = oracle.match(A, B, want_rows=True)
+    assert np.array_equal(pairs, rp)
+    near = int((np.abs(rbest - 0.2) < 1e-3).sum() + (np.abs(rbest / rsecond - 0.8) < 1e-3).sum())
+    assert near > 0  # the case is actually exercised
+
+
+def test_match_ties_nan_and_single_candidate(ctx, oracle):
+    rng = np.random.default_rng(1)
+    B = rng.uniform(-1, 1, (40, 10)).astype(np.float32)
+    B[7] = B[3]
+    B[20] = B[3]          # three identical rows: lowest index wins, ratio 0/0 = NaN -> rejected
+    A = B[[3, 5, 7, 11]].copy()
+    A[1] += np.float32(1e-3)
+    pairs, _ = ctx.match(A, B)
+    rp, _, rbest, rsecond, ridx = oracle.match(A, B, want_rows=True)
+    assert np.array_equal(pairs, rp)
+    assert ridx[0] == 3 and 0 not in pairs[:, 0]  # NaN ratio rejects the exact duplicate
+    # N2 = 1: second stays FLT_MAX -> accepted (my_utilities.h:104)
+    p1, _ = ctx.match(B[:5], B[2:3])
+    r1, _ = oracle.match(B[:5], B[2:3])
+    assert np.array_equal(p1, r1) and len(p1) == 1
+    # NaN / inf descriptors never win
+    A2 = A.copy()
+    A2[2, 4] = np.nan
+    B2 = B.copy()
+    B2[0, 0] = np.inf
+    p3, _ = ctx.match(A2, B2)
+    r3, _ = oracle.match(A2, B2)
+    assert np.array_equal(p3, r3)
+
+
+def test_match_row_sharding(ctx, oracle):
+    """row blocks of A are independent: shards concatenate to the unsharded result"""
+    A, B = synth.descriptors(3001, 2500, seed=4)
+    full, fstats = ctx.match(A, B, idA=np.arange(3001, dtype=np.int32), idB=np.arange(2500, dtype=np.int32))
+    parts, poss, corr = [], 0, 0
+    bounds = [0, 700, 1500, 1501, 3001]
+    for lo, hi in zip(bounds[:-1], bounds[1:]):
+        p, st = ctx.match(A, B, idA=np.arange(3001, dtype=np.int32), idB=np.arange(2500, dtype=np.int32), row_begin=lo,
+                          row_end=hi)
+        parts.append(p)
+        poss += st[0]
+        corr += st[1]
+        rp, _ = oracle.match(A, B, row_begin=lo, row_end=hi)
+        assert np.array_equal(p, rp)
+    assert np.array_equal(np.concatenate(parts), full)
+    assert (poss, corr) == fstats
+
+
+def test_match_empty(ctx):
+    A, B = synth.descriptors(10, 10, seed=1)
+    p, st = ctx.match(A, B, row_begin=4, row_end=4)
+    assert len(p) == 0
+    p, st = ctx.match(A, np.zeros((0, 10), np.float32))
+    assert len(p) == 0
+
+
+def test_match_dataset_kat(ctx, dataset):
+    """exec/match_points_test.cpp as a KAT on the bundled data: every accepted pair has equal id_real"""
+    for i in range(0, 120, 5):
+        a, b = replay.frame(dataset, i), replay.frame(dataset, i + 1)
+        pairs, (possible, correct) = ctx.match(a["desc"], b["desc"], 0.2, 0.8, a["id_real"], b["id_real"])
+        assert correct == len(pairs) == possible
+        assert np.array_equal(a["id_real"][pairs[:, 0]], b["id_real"][pairs[:, 1]])
+
+
+def test_match_large_properties(ctx, oracle):
+    """65536 x 1M (a BASELINE config-4 row shard): oracle on a row sample + structural properties"""
+    import torch
+    n1, n2 = 65536, 1 << 20
+    A, B = synth.descriptors(n1, n2, seed=42)
+    pairs, best, second, idx = _rows_dev(ctx, A, B)
+    assert np.all(np.diff(pairs[:, 0]) > 0)
+    assert np.all(best <= second)
+    sample = np.random.default_rng(0).choice(n1, 48, replace=False)
+    sample.sort()
+    for r in sample:
+        rp, _, rb, rs, ri = oracle.match(A, B, row_begin=int(r), row_end=int(r) + 1, want_rows=True, n_threads=8)
+        assert ri[0] == idx[r] and rb[0] == best[r] and rs[0] == second[r]
+        assert (len(rp) == 1) == bool((pairs[:, 0] == r).any())

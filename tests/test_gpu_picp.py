@@ -1,0 +1,211 @@
+"""GPU parity tests for the PICP path (through the C-ABI) against the CPU oracle.
+
+Bars (BASELINE.json north_star): inlier masks bit-exact; H/b <= 1e-4 norm-relative against the
+float64-accumulated oracle; pose <= 1e-5 absolute after the same number of rounds."""
+import numpy as np
+import pytest
+
+import synth
+from backends import product
+
+pytestmark = pytest.mark.gpu
+
+H_TOL = 1e-4
+POSE_TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    vo = product()
+    c = vo.Context(0)
+    yield c
+    c.close()
+
+
+def _solver(ctx, fr, pose=None):
+    s = ctx.picp()
+    s.set_camera(fr["K"], fr["rows"], fr["cols"], fr["pose0"] if pose is None else pose)
+    s.set_points(fr["world"], fr["image"])
+    s.set_correspondences(fr["pairs"])
+    return s
+
+
+def _check_lin(lin, ref):
+    assert np.array_equal(lin["status"], ref["status"])
+    assert lin["n_inliers"] == ref["n_inliers"]
+    assert lin["n_outliers"] == int((ref["status"] == 2).sum())
+    hs = max(np.abs(ref["H"]).max(), 1e-30)
+    bs = max(np.abs(ref["b"]).max(), 1e-30)
+    assert np.abs(lin["H"] - ref["H"]).max() <= H_TOL * hs
+    assert np.abs(lin["b"] - ref["b"]).max() <= H_TOL * bs
+    assert abs(lin["chi_in"] - ref["chi_in"]) <= H_TOL * max(ref["chi_in"], 1.0)
+    assert abs(lin["chi_out"] - ref["chi_out"]) <= H_TOL * max(ref["chi_out"], 1.0)
+    assert np.array_equal(lin["H"], lin["H"].T)
+
+
+@pytest.mark.parametrize("n,permute", [(1, False), (3, False), (4, False), (5, False), (257, False), (1000, True),
+                                       (65536, False), (200003, True)])
+@pytest.mark.parametrize("thr,keep", [(3000.0, False), (100.0, True), (1000.0, False)])
+def test_linearize_matches_oracle(ctx, oracle, n, permute, thr, keep):
+    fr = synth.picp_frame(n=n, seed=100 + n, permute=permute)
+    s = _solver(ctx, fr)
+    lin = s.linearize(thr, keep, want_status=True, n_pairs=n)
+    ref = oracle.linearize(fr["K"], fr["rows"], fr["cols"], fr["pose0"], fr["world"], fr["image"], fr["pairs"], thr,
+                           keep, accum="f64")
+    _check_lin(lin, ref)
+    s.close()
+
+
+def test_linearize_general_camera_matrix(ctx, oracle):
+    """non-pinhole K (skew, K[2][2] != 1) takes the general arithmetic path"""
+    fr = synth.picp_frame(n=5000, seed=5)
+    K = np.array([[181.5, 0.7, 318.2], [0.01, 179.3, 241.1], [1e-4, -2e-4, 1.01]], np.float32)
+    fr["K"] = K
+    s = _solver(ctx, fr)
+    lin = s.linearize(3000.0, False, want_status=True, n_pairs=5000)
+    ref = oracle.linearize(K, fr["rows"], fr["cols"], fr["pose0"], fr["world"], fr["image"], fr["pairs"], 3000.0, False,
+                           accum="f64")
+    _check_lin(lin, ref)
+    s.close()
+
+
+def test_linearize_edge_values(ctx, oracle):
+    """z<=0, exactly-on-border pixels, chi exactly at the threshold, NaN/inf coordinates."""
+    K = synth.K_REF
+    I = np.eye(4, dtype=np.float32)[:3]
+    world = np.array([[0, 0, 1], [0, 0, 0], [0, 0, -1], [-320 / 180, 0, 1], [319 / 180, 0, 1], [319.5 / 180, 0, 1],
+                      [0, -240 / 180, 1], [0, 239 / 180, 1], [0, 240 / 180, 1], [np.nan, 0, 1], [0, np.inf, 1],
+                      [0, 0, np.inf], [0, 0, np.nan], [1e-30, 1e-30, 1e-38], [0.5, 0.25, 2.0]], np.float32)
+    n = len(world)
+    image = np.zeros((n, 2), np.float32)
+    image[:] = [320, 240]
+    image[0] = [320 + 30, 240 + 40]  # chi = 2500 exactly
+    image[14] = [320 + 45 + 30, 240 + 22.5 + 40]
+    pairs = np.stack([np.arange(n), np.arange(n)], 1).astype(np.int32)
+    for thr in (2500.0, 2499.9998, 3000.0):
+        for keep in (False, True):
+            s = ctx.picp()
+            s.set_camera(K, 480, 640, I)
+            s.set_points(world, image)
+            s.set_correspondences(pairs)
+            lin = s.linearize(thr, keep, want_status=True, n_pairs=n)
+            ref = oracle.linearize(K, 480, 640, I, world, image, pairs, thr, keep, accum="f64")
+            assert np.array_equal(lin["status"], ref["status"]), (thr, keep, lin["status"], ref["status"])
+            assert lin["n_inliers"] == ref["n_inliers"]
+            s.close()
+
+
+def test_empty_and_invalid_correspondences(ctx):
+    vo = product()
+    fr = synth.picp_frame(n=16, seed=1)
+    s = ctx.picp()
+    s.set_camera(fr["K"], 480, 640, fr["pose0"])
+    s.set_points(fr["world"], fr["image"])
+    s.set_correspondences(np.zeros((0, 2), np.int32))
+    lin = s.linearize(3000.0, False)
+    assert lin["n_inliers"] == 0 and not lin["H"].any() and not lin["b"].any()
+    st = s.one_round(3000.0, 1.0, False)  # H = I, b = 0 -> dx = 0 -> pose unchanged
+    assert st.num_inliers == 0
+    assert np.array_equal(s.get_pose(), fr["pose0"])
+    bad = np.array([[0, 0], [3, 99]], np.int32)
+    with pytest.raises(vo.VoError):
+        s.set_correspondences(bad)
+    with pytest.raises(vo.VoError):  # state invalidated by the failed call
+        s.one_round(3000.0, 1.0, False)
+    s.close()
+    s2 = ctx.picp()
+    with pytest.raises(vo.VoError):
+        s2.one_round(3000.0, 1.0, False)  # nothing initialised
+    s2.close()
+
+
+@pytest.mark.parametrize("n,permute,thr,keep,rounds", [(50000, False, 3000.0, False, 10), (50000, True, 100.0, True, 10),
+                                                       (120, False, 3000.0, False, 8), (300000, False, 1000.0, False, 5)])
+def test_rounds_track_oracle(ctx, oracle, n, permute, thr, keep, rounds):
+    """oneRound x rounds: same inlier counts every round, pose within 1e-5 of the float32-sequential
+    oracle, both through the synchronous call and through the enqueue/fetch path."""
+    fr = synth.picp_frame(n=n, seed=n + 1, permute=permute)
+    s = _solver(ctx, fr)
+    s2 = _solver(ctx, fr)
+    pose = fr["pose0"].copy()
+    s2.enqueue_rounds(thr, 1.0, keep, rounds)
+    batch = s2.fetch_stats(rounds)
+    for r in range(rounds):
+        st = s.one_round(thr, 1.0, keep)
+        pose, ci, co, ni = oracle.one_round(fr["K"], fr["rows"], fr["cols"], pose, fr["world"], fr["image"], fr["pairs"],
+                                            thr, 1.0, keep)
+        assert st.num_inliers == ni, r
+        assert batch[r].num_inliers == ni
+        assert batch[r].chi_inliers == st.chi_inliers  # deterministic: two runs are bit-identical
+        assert abs(st.chi_inliers - ci) <= 2e-4 * max(ci, 1.0)
+        assert np.abs(s.get_pose() - pose).max() <= POSE_TOL, r
+    assert np.array_equal(s.get_pose(), s2.get_pose())
+    s.close()
+    s2.close()
+
+
+def test_device_side_convergence_loop(ctx, oracle):
+    """vo_picp_solve == the driver loop of exec/icp_test.cpp:88-107 run with synchronous rounds."""
+    fr = synth.picp_frame(n=20000, seed=11)
+    s = _solver(ctx, fr)
+    done, last = s.solve(3000.0, 1.0, False, max_rounds=50, rel_tol=1e-3)
+    s2 = _solver(ctx, fr)
+    prev = np.float32(np.finfo(np.float32).max)
+    it = 0
+    for it in range(1, 51):
+        st = s2.one_round(3000.0, 1.0, False)
+        cur = np.float32(st.chi_inliers)
+        rel = np.float32(abs(prev - cur)) / prev
+        if rel < np.float32(1e-3):
+            break
+        prev = cur
+    assert done == it
+    assert last.chi_inliers == st.chi_inliers and last.num_inliers == st.num_inliers
+    assert np.array_equal(s.get_pose(), s2.get_pose())
+    s.close()
+    s2.close()
+
+
+def test_device_resident_points(ctx, oracle):
+    """set_points_dev / set_correspondences_dev borrow HBM buffers (torch is only the allocator)."""
+    import torch
+    fr = synth.picp_frame(n=30000, seed=3, permute=True)
+    dw = torch.from_numpy(fr["world"]).cuda()
+    di = torch.from_numpy(fr["image"]).cuda()
+    dp = torch.from_numpy(fr["pairs"]).cuda()
+    torch.cuda.synchronize()
+    s = ctx.picp()
+    s.set_camera(fr["K"], 480, 640, fr["pose0"])
+    s.set_points_dev(dw.data_ptr(), len(fr["world"]), di.data_ptr(), len(fr["image"]))
+    s.set_correspondences_dev(dp.data_ptr(), len(fr["pairs"]))
+    lin = s.linearize(3000.0, False, want_status=True, n_pairs=len(fr["pairs"]))
+    ref = oracle.linearize(fr["K"], 480, 640, fr["pose0"], fr["world"], fr["image"], fr["pairs"], 3000.0, False,
+                           accum="f64")
+    _check_lin(lin, ref)
+    s.close()
+
+
+def test_full_size_properties(ctx):
+    """BASELINE config 2/3 sizes (1M and 10M correspondences): size-independent properties instead of
+    the oracle: linearity of the reduction (H,b of the whole = sum over two halves), determinism,
+    and convergence of 10 rounds to the generator's ground-truth pose."""
+    for n in (1 << 20, 10 * (1 << 20)):
+        fr = synth.picp_frame(n=n, seed=42)
+        s = _solver(ctx, fr)
+        whole = s.linearize(3000.0, False)
+        again = s.linearize(3000.0, False)
+        assert np.array_equal(whole["H"], again["H"]) and np.array_equal(whole["b"], again["b"])
+        half = n // 2
+        parts = []
+        for lo, hi in ((0, half), (half, n)):
+            s.set_correspondences(fr["pairs"][lo:hi])
+            parts.append(s.linearize(3000.0, False))
+        assert parts[0]["n_inliers"] + parts[1]["n_inliers"] == whole["n_inliers"]
+        Hs = parts[0]["H"].astype(np.float64) + parts[1]["H"]
+        assert np.abs(Hs - whole["H"]).max() <= 1e-5 * np.abs(whole["H"]).max()
+        s.set_correspondences(fr["pairs"])
+        s.enqueue_rounds(3000.0, 1.0, False, 10)
+        stats = s.fetch_stats(10)
+        assert stats[-1].num_inliers > 0.85 * n
+        assert np.abs(s.get_pose() - fr["pose_gt"]).max() < 1e-3
+        s.close()
