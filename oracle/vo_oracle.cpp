@@ -74,7 +74,8 @@ struct Lin32 {
 // reference: src/picp_solver.cpp:56-91 (PICPSolver::linearize), float32 sequential
 void linearize32(const float K[9], int rows, int cols, const float T[12], const float* W,
                  const float* Z, const int32_t* pairs, int64_t lo, int64_t hi, float thr,
-                 bool keep, Lin32& o, uint8_t* status) {
+                 bool keep, Lin32& out, uint8_t* status) {
+  Lin32 o;  // thread-local accumulators (the per-thread slots of `parts` share cache lines)
   std::memset(&o, 0, sizeof(o));
   for (int64_t n = lo; n < hi; ++n) {
     int ref_idx = pairs[2 * n], curr_idx = pairs[2 * n + 1];
@@ -103,6 +104,7 @@ void linearize32(const float K[9], int rows, int cols, const float T[12], const 
       }
     }
   }
+  out = o;
 }
 
 // same float32 per-correspondence terms, float64 accumulators (tolerance anchor)
