@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvo_b200.so")
+LIB_PATH = os.environ.get("VO_B200_LIB", os.path.join(_HERE, "libvo_b200.so"))  # override: kernel A/B experiments
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(

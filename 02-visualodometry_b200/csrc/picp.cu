@@ -9,15 +9,18 @@
 //   pairs      int32[2*C]   AoS exactly as IntPairVector (first: image, second: world)
 //   packed     float[5][Cp] SoA stream gathered ONCE per correspondence set by
 //              picp_pack_kernel: wx, wy, wz, zu, zv; Cp = C rounded up to 4.  Every
-//              Gauss-Newton round then streams 20 B/correspondence with LDG.128, each
-//              thread owning 4 consecutive correspondences per step (float4 per plane).
+//              Gauss-Newton round then streams 20 B/correspondence: tiles of 1536
+//              correspondences (5 x 6 KB) are staged into a 4-deep shared-memory ring by one
+//              producer lane with cp.async.bulk (TMA) + mbarrier, and 12 consumer warps read
+//              them back as float4, each thread owning 4 consecutive correspondences per tile
+//              (two pairs; each pair runs through packed f32x2 arithmetic).
 //   partials   float[grid][32]  per-block sums, fixed slot order
 //   result     double[32]   21 upper-triangular H terms, 6 b terms, chi_in, chi_out,
 //              n_inliers, n_outliers (+1 pad): the unit all-reduced across GPUs
 //   dev        PicpDev      pose, round counter, stats ring: the pose never leaves HBM
 //                           between rounds
 //
-// Reduction is deterministic: per-thread float accumulators over a fixed grid-stride
+// Reduction is deterministic: per-thread float accumulators over a fixed tile -> CTA
 // assignment -> warp shuffle tree -> shared-memory sum over warps in warp order ->
 // per-block partial; the block that takes the last ticket sums the partials in block order
 // in float64 (pass 2), then (single GPU) solves the damped 6x6 system and updates the pose
@@ -34,10 +37,21 @@
 
 namespace {
 
-constexpr int kThreads = 256;
+#ifndef VO_LIN_THREADS
+#define VO_LIN_THREADS 384
+#endif
+#ifndef VO_LIN_CTAS
+#define VO_LIN_CTAS 1
+#endif
+#ifndef VO_LIN_STAGES
+#define VO_LIN_STAGES 4
+#endif
+// 384 consumer threads + 1 producer warp, one CTA per SM: the packed even/odd accumulators need ~128
+// registers per thread; measured on B200 (exp/ab.sh): 256x2 spills (110 us), 384x1 67 us, 448x1 74 us.
+constexpr int kThreads = VO_LIN_THREADS;  // consumer threads per CTA of the linearize kernel
 constexpr int kWarps = kThreads / 32;
 constexpr int kSlots = 32;       // partial row: 0..20 H, 21..26 b, 27 chi_in, 28 chi_out, 29 n_in, 30 n_out
-constexpr int kCtasPerSm = 2;
+constexpr int kCtasPerSm = VO_LIN_CTAS;
 
 struct PicpCam {
   float K[9];
@@ -54,6 +68,14 @@ struct PicpDev {
   float rel_tol;  // < 0: no convergence test
   vo_picp_stats stats[VO_PICP_MAX_ROUNDS];
 };
+
+#ifdef VO_PROFILE_STAMPS
+__device__ unsigned long long g_stamps[8];
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define VO_STAMP(i) do { g_stamps[i] = gtime(); } while (0)
+#else
+#define VO_STAMP(i) do { } while (0)
+#endif
 
 struct LinArgs {
   const float* pk;
@@ -75,109 +97,153 @@ __device__ __forceinline__ float dot3_rn(float a0, float b0, float a1, float b1,
 
 __device__ __forceinline__ bool finite_f(float x) { return fabsf(x) <= FLT_MAX; }
 
-// One correspondence. Returns VO_PICP_* and accumulates into acc/n_in/n_out.
-template <bool KEEP, bool PINHOLE>
-__device__ __forceinline__ int picp_point(const PicpCam& cam, const float* __restrict__ T, float thr,
-                                          float px, float py, float pz, float zu, float zv,
-                                          float (&acc)[29], int& n_in, int& n_out) {
-  // ---- exact part: Camera::projectPoint, then e and chi (camera.h:24-36, picp_solver.cpp:36,74)
-  const float c0 = __fadd_rn(T[3], dot3_rn(T[0], px, T[1], py, T[2], pz));
-  const float c1 = __fadd_rn(T[7], dot3_rn(T[4], px, T[5], py, T[6], pz));
-  const float c2 = __fadd_rn(T[11], dot3_rn(T[8], px, T[9], py, T[10], pz));
-  if (c2 <= 0.f) return VO_PICP_SKIPPED;
-  float q0, q1, q2;
-  if (PINHOLE && finite_f(c0) && finite_f(c1)) {
-    // K = [fx 0 cx; 0 fy cy; 0 0 1]: the zero products vanish exactly for finite c
-    q0 = __fadd_rn(__fmul_rn(cam.K[0], c0), __fmul_rn(cam.K[2], c2));
-    q1 = __fadd_rn(__fmul_rn(cam.K[4], c1), __fmul_rn(cam.K[5], c2));
-    q2 = c2;
-  } else {
-    q0 = dot3_rn(cam.K[0], c0, cam.K[1], c1, cam.K[2], c2);
-    q1 = dot3_rn(cam.K[3], c0, cam.K[4], c1, cam.K[5], c2);
-    q2 = dot3_rn(cam.K[6], c0, cam.K[7], c1, cam.K[8], c2);
-  }
-  const float iz = __frcp_rn(q2);  // == (float)(1./(double)q2): correctly rounded reciprocal
-  const float u = __fmul_rn(q0, iz);
-  const float v = __fmul_rn(q1, iz);
-  if (u < 0.f || u > cam.umax) return VO_PICP_SKIPPED;
-  if (v < 0.f || v > cam.vmax) return VO_PICP_SKIPPED;
-  const float e0 = __fsub_rn(u, zu);
-  const float e1 = __fsub_rn(v, zv);
-  const float chi = __fadd_rn(__fmul_rn(e0, e0), __fmul_rn(e1, e1));
-  float lambda = 1.f;
+// ---- packed f32x2 arithmetic (sm_100a): one instruction, two IEEE round-to-nearest float ops.
+// The FP32 pipe retires the same lanes per clock either way; packing halves the issue slots, which
+// is what bounds this kernel (profiles/r01_picp_linearize_v1.md).
+typedef unsigned long long f2;
+__device__ __forceinline__ f2 pack2(float lo, float hi) {
+  f2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
+  f2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) {
+  f2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f2 neg2(f2 a) { return a ^ 0x8000000080000000ull; }
+
+// Exact projection, error and chi of ONE correspondence (camera.h:24-36, picp_solver.cpp:32-36,74):
+// every operation is an explicitly rounded float32 op in the reference's order, never contracted.
+// Straight-line on the common path so that the two points of a pair interleave in the pipeline.
+struct PointTerms {
+  float c0, c1, c2, q0, q1, iz, e0, e1, chi;
   int st;
-  if (chi > thr) {
-    acc[28] += chi;
-    n_out++;
-    if (!KEEP) return VO_PICP_OUTLIER;
-    lambda = __fsqrt_rn(__fdiv_rn(thr, chi));
-    st = VO_PICP_OUTLIER;
-  } else {
-    acc[27] += chi;
-    n_in++;
-    st = VO_PICP_INLIER;
-  }
-  // ---- tolerance part: J = (Jp*K)*[I | skew(-c)], H += lambda J^T J, b += lambda J^T e
-  const float iz2 = iz * iz;
-  const float m0 = -q0 * iz2, m1 = -q1 * iz2;
+};
+
+template <bool PINHOLE>
+__device__ __forceinline__ PointTerms picp_project(const PicpCam& cam, const float* __restrict__ T, float thr,
+                                                   float px, float py, float pz, float zu, float zv, bool valid) {
+  PointTerms t;
+  t.c0 = __fadd_rn(T[3], dot3_rn(T[0], px, T[1], py, T[2], pz));
+  t.c1 = __fadd_rn(T[7], dot3_rn(T[4], px, T[5], py, T[6], pz));
+  t.c2 = __fadd_rn(T[11], dot3_rn(T[8], px, T[9], py, T[10], pz));
+  // Shortcut (pinhole K = [fx 0 cx; 0 fy cy; 0 0 1], finite c0/c1, 1e-30 <= c2 <= 1e30):
+  //  * 0*c1 and 0*c0 are exact zeros, so q = (fx*c0 + cx*c2, fy*c1 + cy*c2, c2) bit for bit;
+  //  * rcp.approx + one Newton step on FMA is the correctly rounded 1/c2 for normal-range
+  //    operands (the sequence __frcp_rn itself runs once its range check has passed).
+  const bool shortcut = PINHOLE && (t.c2 >= 1e-30f) && (t.c2 <= 1e30f) && finite_f(t.c0) && finite_f(t.c1);
   if (PINHOLE) {
-    const float a = iz * cam.K[0], d = iz * cam.K[4];
-    const float g = fmaf(iz, cam.K[2], m0), h = fmaf(iz, cam.K[5], m1);
-    const float j3 = g * c1, j4 = fmaf(a, c2, -g * c0), j5 = -a * c1;
-    const float k3 = fmaf(h, c1, -d * c2), k4 = -h * c0, k5 = d * c0;
-    const float as = KEEP ? a * lambda : a, ds = KEEP ? d * lambda : d;
-    const float gs = KEEP ? g * lambda : g, hs = KEEP ? h * lambda : h;
-    const float j3s = KEEP ? j3 * lambda : j3, j4s = KEEP ? j4 * lambda : j4, j5s = KEEP ? j5 * lambda : j5;
-    const float k3s = KEEP ? k3 * lambda : k3, k4s = KEEP ? k4 * lambda : k4, k5s = KEEP ? k5 * lambda : k5;
-    acc[0] = fmaf(as, a, acc[0]);  // H00 ; H01 (acc[1]) is structurally zero
-    acc[2] = fmaf(as, g, acc[2]);
-    acc[3] = fmaf(as, j3, acc[3]);
-    acc[4] = fmaf(as, j4, acc[4]);
-    acc[5] = fmaf(as, j5, acc[5]);
-    acc[6] = fmaf(ds, d, acc[6]);  // H11
-    acc[7] = fmaf(ds, h, acc[7]);
-    acc[8] = fmaf(ds, k3, acc[8]);
-    acc[9] = fmaf(ds, k4, acc[9]);
-    acc[10] = fmaf(ds, k5, acc[10]);
-    acc[11] = fmaf(gs, g, fmaf(hs, h, acc[11]));  // H22
-    acc[12] = fmaf(gs, j3, fmaf(hs, k3, acc[12]));
-    acc[13] = fmaf(gs, j4, fmaf(hs, k4, acc[13]));
-    acc[14] = fmaf(gs, j5, fmaf(hs, k5, acc[14]));
-    acc[15] = fmaf(j3s, j3, fmaf(k3s, k3, acc[15]));  // H33
-    acc[16] = fmaf(j3s, j4, fmaf(k3s, k4, acc[16]));
-    acc[17] = fmaf(j3s, j5, fmaf(k3s, k5, acc[17]));
-    acc[18] = fmaf(j4s, j4, fmaf(k4s, k4, acc[18]));  // H44
-    acc[19] = fmaf(j4s, j5, fmaf(k4s, k5, acc[19]));
-    acc[20] = fmaf(j5s, j5, fmaf(k5s, k5, acc[20]));  // H55
-    acc[21] = fmaf(as, e0, acc[21]);
-    acc[22] = fmaf(ds, e1, acc[22]);
-    acc[23] = fmaf(gs, e0, fmaf(hs, e1, acc[23]));
-    acc[24] = fmaf(j3s, e0, fmaf(k3s, e1, acc[24]));
-    acc[25] = fmaf(j4s, e0, fmaf(k4s, e1, acc[25]));
-    acc[26] = fmaf(j5s, e0, fmaf(k5s, e1, acc[26]));
+    t.q0 = __fadd_rn(__fmul_rn(cam.K[0], t.c0), __fmul_rn(cam.K[2], t.c2));
+    t.q1 = __fadd_rn(__fmul_rn(cam.K[4], t.c1), __fmul_rn(cam.K[5], t.c2));
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t.c2));
+    t.iz = fmaf(r, fmaf(-t.c2, r, 1.f), r);
+  }
+  if (!shortcut && !(t.c2 <= 0.f)) {
+    // rare: the reference's arithmetic verbatim (general K, IEEE reciprocal)
+    t.q0 = dot3_rn(cam.K[0], t.c0, cam.K[1], t.c1, cam.K[2], t.c2);
+    t.q1 = dot3_rn(cam.K[3], t.c0, cam.K[4], t.c1, cam.K[5], t.c2);
+    t.iz = __frcp_rn(dot3_rn(cam.K[6], t.c0, cam.K[7], t.c1, cam.K[8], t.c2));  // == (float)(1./(double)q2)
+  }
+  const float u = __fmul_rn(t.q0, t.iz);
+  const float v = __fmul_rn(t.q1, t.iz);
+  // camera.h:27,31-34 with their NaN behaviour: a NaN compares false and stays "inside"
+  // (`valid` is false only for the padding lanes of the last quad of the stream)
+  const bool inside = valid && !(t.c2 <= 0.f) && !(u < 0.f) && !(u > cam.umax) && !(v < 0.f) && !(v > cam.vmax);
+  t.e0 = __fsub_rn(u, zu);
+  t.e1 = __fsub_rn(v, zv);
+  t.chi = __fadd_rn(__fmul_rn(t.e0, t.e0), __fmul_rn(t.e1, t.e1));
+  t.st = inside ? ((t.chi > thr) ? VO_PICP_OUTLIER : VO_PICP_INLIER) : VO_PICP_SKIPPED;
+  return t;
+}
+
+// Two correspondences: exact part per point, then J, H += lambda J^T J and b += lambda J^T e in packed
+// f32x2 (lane 0 = first point, lane 1 = second; acc2[k] holds the two lanes' partial sums of slot k).
+// Points that do not contribute get all-zero Jacobian rows instead of a branch.
+template <bool KEEP, bool PINHOLE>
+__device__ __forceinline__ void picp_pair(const PicpCam& cam, const float* __restrict__ T, float thr,
+                                          float px0, float py0, float pz0, float zu0, float zv0,
+                                          float px1, float py1, float pz1, float zu1, float zv1, bool v0, bool v1,
+                                          f2 (&acc2)[29], int& n_in, int& n_out, int& st0, int& st1) {
+  PointTerms t0 = picp_project<PINHOLE>(cam, T, thr, px0, py0, pz0, zu0, zv0, v0);
+  PointTerms t1 = picp_project<PINHOLE>(cam, T, thr, px1, py1, pz1, zu1, zv1, v1);
+  st0 = t0.st;
+  st1 = t1.st;
+  const bool in0 = t0.st == VO_PICP_INLIER, in1 = t1.st == VO_PICP_INLIER;
+  const bool out0 = t0.st == VO_PICP_OUTLIER, out1 = t1.st == VO_PICP_OUTLIER;
+  n_in += (int)in0 + (int)in1;
+  n_out += (int)out0 + (int)out1;
+  acc2[27] = fma2(pack2(in0 ? 1.f : 0.f, in1 ? 1.f : 0.f), pack2(in0 ? t0.chi : 0.f, in1 ? t1.chi : 0.f), acc2[27]);
+  acc2[28] = fma2(pack2(out0 ? 1.f : 0.f, out1 ? 1.f : 0.f), pack2(out0 ? t0.chi : 0.f, out1 ? t1.chi : 0.f), acc2[28]);
+  const bool use0 = in0 || (KEEP && out0), use1 = in1 || (KEEP && out1);
+  // contribution weight: 0 (dropped), 1 (inlier) or lambda = sqrt(thr/chi) (kept outlier, picp_solver.cpp:78)
+  float w0 = use0 ? 1.f : 0.f, w1 = use1 ? 1.f : 0.f;
+  if (KEEP) {
+    if (out0) w0 = __fsqrt_rn(__fdiv_rn(thr, t0.chi));
+    if (out1) w1 = __fsqrt_rn(__fdiv_rn(thr, t1.chi));
+  }
+  // zero the inputs of dropped points so that no inf/NaN of theirs reaches the sums
+  const f2 iz = pack2(use0 ? t0.iz : 0.f, use1 ? t1.iz : 0.f);
+  const f2 nq0 = pack2(use0 ? -t0.q0 : 0.f, use1 ? -t1.q0 : 0.f);
+  const f2 nq1 = pack2(use0 ? -t0.q1 : 0.f, use1 ? -t1.q1 : 0.f);
+  const f2 c0 = pack2(use0 ? t0.c0 : 0.f, use1 ? t1.c0 : 0.f);
+  const f2 c1 = pack2(use0 ? t0.c1 : 0.f, use1 ? t1.c1 : 0.f);
+  const f2 c2 = pack2(use0 ? t0.c2 : 0.f, use1 ? t1.c2 : 0.f);
+  const f2 nc0 = neg2(c0), nc1 = neg2(c1), nc2 = neg2(c2);
+  const f2 e0 = pack2(use0 ? t0.e0 : 0.f, use1 ? t1.e0 : 0.f);
+  const f2 e1 = pack2(use0 ? t0.e1 : 0.f, use1 ? t1.e1 : 0.f);
+  const f2 w = pack2(w0, w1);
+  // ---- tolerance part: J = (Jp*K)*[I | skew(-c)]
+  const f2 iz2 = mul2(iz, iz);
+  const f2 m0 = mul2(nq0, iz2), m1 = mul2(nq1, iz2);  // -q*iz^2
+  f2 J0[6], J1[6];
+  if (PINHOLE) {
+    const f2 fx = pack2(cam.K[0], cam.K[0]), fy = pack2(cam.K[4], cam.K[4]);
+    const f2 cx = pack2(cam.K[2], cam.K[2]), cy = pack2(cam.K[5], cam.K[5]);
+    const f2 a = mul2(iz, fx), d = mul2(iz, fy);
+    const f2 g = fma2(iz, cx, m0), h = fma2(iz, cy, m1);
+    J0[0] = a; J0[1] = 0ull; J0[2] = g;
+    J0[3] = mul2(g, c1); J0[4] = fma2(g, nc0, mul2(a, c2)); J0[5] = mul2(a, nc1);
+    J1[0] = 0ull; J1[1] = d; J1[2] = h;
+    J1[3] = fma2(d, nc2, mul2(h, c1)); J1[4] = mul2(h, nc0); J1[5] = mul2(d, c0);
   } else {
-    float J0[6], J1[6];
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
-      J0[j] = fmaf(iz, cam.K[j], m0 * cam.K[6 + j]);
-      J1[j] = fmaf(iz, cam.K[3 + j], m1 * cam.K[6 + j]);
+      J0[j] = fma2(iz, pack2(cam.K[j], cam.K[j]), mul2(m0, pack2(cam.K[6 + j], cam.K[6 + j])));
+      J1[j] = fma2(iz, pack2(cam.K[3 + j], cam.K[3 + j]), mul2(m1, pack2(cam.K[6 + j], cam.K[6 + j])));
     }
-    J0[3] = fmaf(J0[2], c1, -J0[1] * c2);
-    J0[4] = fmaf(J0[0], c2, -J0[2] * c0);
-    J0[5] = fmaf(J0[1], c0, -J0[0] * c1);
-    J1[3] = fmaf(J1[2], c1, -J1[1] * c2);
-    J1[4] = fmaf(J1[0], c2, -J1[2] * c0);
-    J1[5] = fmaf(J1[1], c0, -J1[0] * c1);
-    int k = 0;
-#pragma unroll
-    for (int i = 0; i < 6; ++i) {
-      const float s0 = KEEP ? J0[i] * lambda : J0[i], s1 = KEEP ? J1[i] * lambda : J1[i];
-#pragma unroll
-      for (int j = i; j < 6; ++j, ++k) acc[k] = fmaf(s0, J0[j], fmaf(s1, J1[j], acc[k]));
-      acc[21 + i] = fmaf(s0, e0, fmaf(s1, e1, acc[21 + i]));
-    }
+    J0[3] = fma2(J0[1], nc2, mul2(J0[2], c1));
+    J0[4] = fma2(J0[2], nc0, mul2(J0[0], c2));
+    J0[5] = fma2(J0[0], nc1, mul2(J0[1], c0));
+    J1[3] = fma2(J1[1], nc2, mul2(J1[2], c1));
+    J1[4] = fma2(J1[2], nc0, mul2(J1[0], c2));
+    J1[5] = fma2(J1[0], nc1, mul2(J1[1], c0));
   }
-  return st;
+  // ---- H += w J^T J (21 upper-triangular slots), b += w J^T e; structural zeros of the pinhole
+  // Jacobian (J0[1] = J1[0] = 0) are skipped at compile time
+  int k = 0;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    const bool z0 = PINHOLE && i == 1, z1 = PINHOLE && i == 0;  // row entries known to be zero
+    const f2 s0 = KEEP ? mul2(J0[i], w) : J0[i], s1 = KEEP ? mul2(J1[i], w) : J1[i];
+#pragma unroll
+    for (int j = i; j < 6; ++j, ++k) {
+      const bool y0 = z0 || (PINHOLE && j == 1), y1 = z1 || (PINHOLE && j == 0);
+      if (!y0) acc2[k] = fma2(s0, J0[j], acc2[k]);
+      if (!y1) acc2[k] = fma2(s1, J1[j], acc2[k]);
+    }
+    if (!z0) acc2[21 + i] = fma2(s0, e0, acc2[21 + i]);
+    if (!z1) acc2[21 + i] = fma2(s1, e1, acc2[21 + i]);
+  }
 }
 
 // ------------------------------------------------------------------ 6x6 solve + pose update
@@ -238,26 +304,75 @@ __device__ void mat3_mul_rn(const float* A, const float* B, float* C) {
       C[3 * i + j] = dot3_rn(A[3 * i], B[j], A[3 * i + 1], B[3 + j], A[3 * i + 2], B[6 + j]);
 }
 
+// Unpivoted LDL^T of a symmetric positive definite 6x6, fully unrolled so that every entry lives in
+// a register.  H + damping*I with damping > 0 is SPD (H is a sum of J^T J), so diagonal pivoting is
+// not needed for stability; the result differs from Eigen's pivoted LDLT by float rounding only
+// (covered by the 1e-5 pose tolerance).  damping <= 0 keeps the pivoted restatement above.
+__device__ __forceinline__ void ldl_solve6_spd(float (&m)[6][6], float (&d)[6]) {
+  float D[6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    float t[6];
+    float dj = m[j][j];
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+      if (k < j) {
+        t[k] = m[j][k] * D[k];
+        dj = fmaf(-m[j][k], t[k], dj);
+      }
+    D[j] = dj;
+    const float inv = __fdiv_rn(1.f, dj);
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+      if (i > j) {
+        float v = m[i][j];
+#pragma unroll
+        for (int k = 0; k < 6; ++k)
+          if (k < j) v = fmaf(-m[i][k], t[k], v);
+        m[i][j] = v * inv;
+      }
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+#pragma unroll
+    for (int j = 0; j < 6; ++j)
+      if (j < i) d[i] = fmaf(-m[i][j], d[j], d[i]);
+#pragma unroll
+  for (int i = 0; i < 6; ++i) d[i] = __fdiv_rn(d[i], D[i]);
+#pragma unroll
+  for (int i = 5; i >= 0; --i)
+#pragma unroll
+    for (int j = 0; j < 6; ++j)
+      if (j > i) d[i] = fmaf(-m[j][i], d[j], d[i]);
+}
+
 // result[32] (double) -> damped solve -> pose update, stats ring, convergence flag. One thread.
 __device__ void picp_solve_update(const double* __restrict__ res, float damping, PicpDev* dev) {
   float m[6][6], rhs[6];
-  int k = 0;
-  for (int i = 0; i < 6; ++i)
-    for (int j = i; j < 6; ++j, ++k) {
-      const float h = (float)res[k];
-      m[i][j] = h;
-      m[j][i] = h;
-    }
+  {
+    int k = 0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+      for (int j = 0; j < 6; ++j)
+        if (j >= i) {
+          const float h = (float)res[k++];
+          m[i][j] = h;
+          m[j][i] = h;
+        }
+  }
+#pragma unroll
   for (int i = 0; i < 6; ++i) {
     m[i][i] = __fadd_rn(m[i][i], damping);  // H += I*damping (picp_solver.cpp:96)
     rhs[i] = -(float)res[21 + i];
   }
-  ldlt_solve6_dev(m, rhs);
-  // libm cos/sin of a float argument: evaluate in double and round (matches cosf to the last bit
-  // except in astronomically rare double-rounding cases)
-  const float cx = (float)cos((double)rhs[3]), sx = (float)sin((double)rhs[3]);
-  const float cy = (float)cos((double)rhs[4]), sy = (float)sin((double)rhs[4]);
-  const float cz = (float)cos((double)rhs[5]), sz = (float)sin((double)rhs[5]);
+  if (damping > 0.f) ldl_solve6_spd(m, rhs);
+  else ldlt_solve6_dev(m, rhs);
+  // Rx(dx3) Ry(dx4) Rz(dx5) (defs.h:100-136); sinf/cosf are within 2 ulp of libm's
+  float sx, cx, sy, cy, sz, cz;
+  sincosf(rhs[3], &sx, &cx);
+  sincosf(rhs[4], &sy, &cy);
+  sincosf(rhs[5], &sz, &cz);
   const float Rx[9] = {1, 0, 0, 0, cx, -sx, 0, sx, cx};
   const float Ry[9] = {cy, 0, sy, 0, 1, 0, -sy, 0, cy};
   const float Rz[9] = {cz, -sz, 0, sz, cz, 0, 0, 0, 1};
@@ -287,79 +402,169 @@ __device__ void picp_solve_update(const double* __restrict__ res, float damping,
   }
 }
 
+// ------------------------------------------------------------------ mbarrier / bulk-copy (TMA) primitives
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// producer-side wait: a long suspend-time hint keeps the single producer lane from stealing issue
+// slots from the consumer warps of its scheduler while the ring is full
+__device__ __forceinline__ void mbar_wait_relaxed(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAITR_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+      "@p bra DONER_%=;\n"
+      "bra WAITR_%=;\n"
+      "DONER_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity), "r"(20000u)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// 1-D bulk copy global -> shared through the TMA engine, completion counted on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
 // ------------------------------------------------------------------ linearize + reduce
+// Tile ring: kStages x (5 planes x kTile floats) in shared memory, filled by one producer lane
+// with cp.async.bulk and consumed by 8 warps; tile t belongs to CTA (t mod gridDim.x) and quad
+// `threadIdx.x` of every tile to the same thread, so the summation order is fixed.
+constexpr int kTile = 4 * kThreads;  // correspondences per tile
+constexpr int kStages = VO_LIN_STAGES;
+constexpr int kLinThreads = kThreads + 32;  // 8 consumer warps + 1 producer warp
+constexpr size_t kLinSmemBytes = (size_t)kStages * 5 * kTile * sizeof(float);
+
 template <bool KEEP, bool STATUS, bool PINHOLE>
-__global__ void __launch_bounds__(kThreads, kCtasPerSm) picp_linearize_kernel(const LinArgs a) {
+__global__ void __launch_bounds__(kLinThreads, kCtasPerSm) picp_linearize_kernel(const LinArgs a) {
   if (a.dev->stop) return;  // a converged device-side loop turns the remaining launches into no-ops
+  if (blockIdx.x == 0 && threadIdx.x == 0) VO_STAMP(0);
+  extern __shared__ __align__(128) float s_tiles[];
+  __shared__ __align__(8) unsigned long long s_full[kStages], s_empty[kStages];
   __shared__ float s_pose[12];
   __shared__ float s_part[kWarps][kSlots];
   __shared__ double s_fin[kWarps][kSlots];
   __shared__ int s_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x < 12) s_pose[threadIdx.x] = a.dev->pose[threadIdx.x];
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&s_full[s], 1);        // the producer's arrive.expect_tx
+      mbar_init(&s_empty[s], kWarps);  // one arrival per consumer warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   __syncthreads();
-  float T[12];
-#pragma unroll
-  for (int i = 0; i < 12; ++i) T[i] = s_pose[i];
 
-  float acc[29];
+  const long long n_tiles = (a.n + kTile - 1) / kTile;
+  f2 acc2[29];
 #pragma unroll
-  for (int i = 0; i < 29; ++i) acc[i] = 0.f;
+  for (int i = 0; i < 29; ++i) acc2[i] = 0ull;
   int n_in = 0, n_out = 0;
 
-  const long long n_quads = (a.n + 3) >> 2;
-  const long long step = (long long)gridDim.x * kThreads;
-  const float4* __restrict__ p0 = reinterpret_cast<const float4*>(a.pk);
-  const float4* __restrict__ p1 = reinterpret_cast<const float4*>(a.pk + a.stride);
-  const float4* __restrict__ p2 = reinterpret_cast<const float4*>(a.pk + 2 * a.stride);
-  const float4* __restrict__ p3 = reinterpret_cast<const float4*>(a.pk + 3 * a.stride);
-  const float4* __restrict__ p4 = reinterpret_cast<const float4*>(a.pk + 4 * a.stride);
-
-  long long q = (long long)blockIdx.x * kThreads + threadIdx.x;
-  float4 wx, wy, wz, zu, zv;
-  if (q < n_quads) {
-    wx = ldg_stream4(p0 + q); wy = ldg_stream4(p1 + q); wz = ldg_stream4(p2 + q);
-    zu = ldg_stream4(p3 + q); zv = ldg_stream4(p4 + q);
-  }
-  while (q < n_quads) {
-    const long long qn = q + step;
-    float4 nwx, nwy, nwz, nzu, nzv;
-    if (qn < n_quads) {  // software prefetch of the next quad: 160 B in flight per thread
-      nwx = ldg_stream4(p0 + qn); nwy = ldg_stream4(p1 + qn); nwz = ldg_stream4(p2 + qn);
-      nzu = ldg_stream4(p3 + qn); nzv = ldg_stream4(p4 + qn);
-    }
-    const long long base = q << 2;
-    int s0 = VO_PICP_SKIPPED, s1 = VO_PICP_SKIPPED, s2 = VO_PICP_SKIPPED, s3 = VO_PICP_SKIPPED;
-    s0 = picp_point<KEEP, PINHOLE>(a.cam, T, a.thr, wx.x, wy.x, wz.x, zu.x, zv.x, acc, n_in, n_out);
-    if (base + 1 < a.n) s1 = picp_point<KEEP, PINHOLE>(a.cam, T, a.thr, wx.y, wy.y, wz.y, zu.y, zv.y, acc, n_in, n_out);
-    if (base + 2 < a.n) s2 = picp_point<KEEP, PINHOLE>(a.cam, T, a.thr, wx.z, wy.z, wz.z, zu.z, zv.z, acc, n_in, n_out);
-    if (base + 3 < a.n) s3 = picp_point<KEEP, PINHOLE>(a.cam, T, a.thr, wx.w, wy.w, wz.w, zu.w, zv.w, acc, n_in, n_out);
-    if (STATUS) {
-      if (base + 3 < a.n) {
-        *reinterpret_cast<uchar4*>(a.status + base) = make_uchar4(s0, s1, s2, s3);
-      } else {
-        a.status[base] = s0;
-        if (base + 1 < a.n) a.status[base + 1] = s1;
-        if (base + 2 < a.n) a.status[base + 2] = s2;
+  if (warp == kWarps) {
+    // ---------------- producer: one elected lane keeps the ring full
+    if (lane == 0) {
+      int it = 0;
+      for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+        const int stage = it % kStages;
+        const unsigned phase = (unsigned)(it / kStages) & 1u;
+        mbar_wait_relaxed(&s_empty[stage], phase ^ 1u);
+        const long long first = t * kTile;
+        const long long left = ((a.n + 3) & ~3ll) - first;
+        const unsigned bytes = (unsigned)((left < kTile ? left : kTile) * sizeof(float));
+        float* dst = s_tiles + (size_t)stage * 5 * kTile;
+        mbar_arrive_expect_tx(&s_full[stage], 5u * bytes);
+#pragma unroll
+        for (int p = 0; p < 5; ++p) bulk_g2s(dst + p * kTile, a.pk + p * a.stride + first, bytes, &s_full[stage]);
       }
     }
-    wx = nwx; wy = nwy; wz = nwz; zu = nzu; zv = nzv;
-    q = qn;
-  }
-
-  // ---- pass 1: warp shuffle tree, then warps summed in warp order
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  } else {
+    // ---------------- consumers
+    float T[12];
 #pragma unroll
-  for (int i = 0; i < 29; ++i) acc[i] = warp_sum(acc[i]);
-  n_in = warp_sum_i(n_in);
-  n_out = warp_sum_i(n_out);
-  if (lane == 0) {
+    for (int i = 0; i < 12; ++i) T[i] = s_pose[i];
+    int it = 0;
+    for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+      const int stage = it % kStages;
+      const unsigned phase = (unsigned)(it / kStages) & 1u;
+      mbar_wait(&s_full[stage], phase);
+      const float4* tile = reinterpret_cast<const float4*>(s_tiles + (size_t)stage * 5 * kTile);
+      const long long base = t * kTile + 4ll * threadIdx.x;
+      float4 wx, wy, wz, zu, zv;
+      const bool any = base < a.n;
+      if (any) {
+        wx = tile[threadIdx.x];
+        wy = tile[kThreads + threadIdx.x];
+        wz = tile[2 * kThreads + threadIdx.x];
+        zu = tile[3 * kThreads + threadIdx.x];
+        zv = tile[4 * kThreads + threadIdx.x];
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[stage]);  // values are in registers: hand the stage back
+      if (!any) continue;
+      int s0, s1, s2, s3;
+      const long long left = a.n - base;  // >= 1; < 4 only in the last quad of the stream
+      picp_pair<KEEP, PINHOLE>(a.cam, T, a.thr, wx.x, wy.x, wz.x, zu.x, zv.x, wx.y, wy.y, wz.y, zu.y, zv.y, true, left > 1,
+                               acc2, n_in, n_out, s0, s1);
+      picp_pair<KEEP, PINHOLE>(a.cam, T, a.thr, wx.z, wy.z, wz.z, zu.z, zv.z, wx.w, wy.w, wz.w, zu.w, zv.w, left > 2,
+                               left > 3, acc2, n_in, n_out, s2, s3);
+      if (STATUS) {
+        if (base + 3 < a.n) {
+          *reinterpret_cast<uchar4*>(a.status + base) = make_uchar4(s0, s1, s2, s3);
+        } else {
+          a.status[base] = s0;
+          if (base + 1 < a.n) a.status[base + 1] = s1;
+          if (base + 2 < a.n) a.status[base + 2] = s2;
+        }
+      }
+    }
+    float acc[29];
 #pragma unroll
-    for (int i = 0; i < 29; ++i) s_part[warp][i] = acc[i];
-    s_part[warp][29] = __int_as_float(n_in);
-    s_part[warp][30] = __int_as_float(n_out);
-    s_part[warp][31] = 0.f;
+    for (int i = 0; i < 29; ++i) {
+      float lo, hi;
+      unpack2(acc2[i], lo, hi);
+      acc[i] = lo + hi;
+    }
+    // ---- pass 1: warp shuffle tree, then warps summed in warp order
+#pragma unroll
+    for (int i = 0; i < 29; ++i) acc[i] = warp_sum(acc[i]);
+    n_in = warp_sum_i(n_in);
+    n_out = warp_sum_i(n_out);
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < 29; ++i) s_part[warp][i] = acc[i];
+      s_part[warp][29] = __int_as_float(n_in);
+      s_part[warp][30] = __int_as_float(n_out);
+      s_part[warp][31] = 0.f;
+    }
   }
   __syncthreads();
+  if (blockIdx.x == 0 && threadIdx.x == 0) VO_STAMP(1);
   if (threadIdx.x < kSlots) {
     const int c = threadIdx.x;
     float v;
@@ -382,15 +587,25 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) picp_linearize_kernel(co
   }
   __syncthreads();
   if (!s_last) return;
+  if (threadIdx.x == 0) VO_STAMP(2);
   __threadfence();
-  {
+  if (threadIdx.x < kThreads) {
     const int c = threadIdx.x & 31, chunk = threadIdx.x >> 5;
     double v = 0.0;
     long long iv = 0;
-    for (unsigned b = chunk; b < gridDim.x; b += kWarps) {
-      const float x = __ldcg(a.partials + (size_t)b * kSlots + c);
-      if (c == 29 || c == 30) iv += __float_as_int(x);
-      else v += (double)x;
+    constexpr int kBatch = 8;  // independent L2 loads in flight per thread (the sum order stays fixed)
+    for (unsigned b0 = chunk; b0 < gridDim.x; b0 += kWarps * kBatch) {
+      float x[kBatch];
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        const unsigned b = b0 + u * kWarps;
+        x[u] = (b < gridDim.x) ? __ldcg(a.partials + (size_t)b * kSlots + c) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        if (c == 29 || c == 30) iv += __float_as_int(x[u]);
+        else v += (double)x[u];
+      }
     }
     s_fin[chunk][c] = (c == 29 || c == 30) ? (double)iv : v;
   }
@@ -403,8 +618,10 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) picp_linearize_kernel(co
   }
   __syncthreads();
   if (threadIdx.x == 0) {
+    VO_STAMP(3);
     a.dev->ticket = 0;
     if (a.fuse_solve) picp_solve_update(s_fin[0], a.damping, a.dev);
+    VO_STAMP(4);
   }
 }
 
@@ -419,7 +636,12 @@ __global__ void __launch_bounds__(256) picp_pack_kernel(const int2* __restrict__
                                                         const float* __restrict__ image, long long n_image,
                                                         float* __restrict__ pk, long long stride, PicpDev* dev) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  if (i >= n) {
+    if (i < ((n + 3) & ~3ll)) {  // padding lanes of the last quad: finite values, masked out by the consumer
+      pk[i] = 0.f; pk[stride + i] = 0.f; pk[2 * stride + i] = 0.f; pk[3 * stride + i] = 0.f; pk[4 * stride + i] = 0.f;
+    }
+    return;
+  }
   const int2 pr = __ldg(pairs + i);  // (first: image index, second: world index)
   if (pr.x < 0 || pr.x >= n_image || pr.y < 0 || pr.y >= n_world) {
     dev->bad_index = 1;
@@ -441,6 +663,25 @@ __global__ void picp_reset_kernel(PicpDev* dev, float rel_tol) {
   dev->stop = 0;
   dev->prev_chi = FLT_MAX;
   dev->rel_tol = rel_tol;
+}
+
+template <bool KEEP, bool STATUS, bool PINHOLE>
+cudaError_t lin_opt_in() {
+  return cudaFuncSetAttribute(picp_linearize_kernel<KEEP, STATUS, PINHOLE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)kLinSmemBytes);
+}
+
+cudaError_t lin_opt_in_all() {
+  cudaError_t e = cudaSuccess;
+  if (e == cudaSuccess) e = lin_opt_in<false, false, false>();
+  if (e == cudaSuccess) e = lin_opt_in<false, false, true>();
+  if (e == cudaSuccess) e = lin_opt_in<false, true, false>();
+  if (e == cudaSuccess) e = lin_opt_in<false, true, true>();
+  if (e == cudaSuccess) e = lin_opt_in<true, false, false>();
+  if (e == cudaSuccess) e = lin_opt_in<true, false, true>();
+  if (e == cudaSuccess) e = lin_opt_in<true, true, false>();
+  if (e == cudaSuccess) e = lin_opt_in<true, true, true>();
+  return e;
 }
 
 bool is_pinhole(const float K[9]) {
@@ -488,8 +729,7 @@ int grow(vo_ctx* ctx, void** p, size_t* cap, size_t bytes) {
 }
 
 int grid_for(const vo_picp* s) {
-  const long long quads = (s->n_pairs + 3) / 4;
-  long long g = (quads + kThreads - 1) / kThreads;
+  long long g = (s->n_pairs + kTile - 1) / kTile;  // one tile = kTile correspondences
   if (g < 1) g = 1;
   if (g > s->max_grid) g = s->max_grid;
   return (int)g;
@@ -497,8 +737,8 @@ int grid_for(const vo_picp* s) {
 
 template <bool KEEP, bool STATUS>
 void launch_lin2(bool pinhole, int grid, cudaStream_t st, const LinArgs& a) {
-  if (pinhole) picp_linearize_kernel<KEEP, STATUS, true><<<grid, kThreads, 0, st>>>(a);
-  else picp_linearize_kernel<KEEP, STATUS, false><<<grid, kThreads, 0, st>>>(a);
+  if (pinhole) picp_linearize_kernel<KEEP, STATUS, true><<<grid, kLinThreads, kLinSmemBytes, st>>>(a);
+  else picp_linearize_kernel<KEEP, STATUS, false><<<grid, kLinThreads, kLinSmemBytes, st>>>(a);
 }
 
 int launch_linearize(vo_picp* s, float thr, float damping, bool keep, bool status, bool fuse_solve) {
@@ -569,7 +809,8 @@ int vo_picp_create(vo_ctx* ctx, vo_picp** out) {
   if (!s) return VO_ERR_NOMEM;
   s->ctx = ctx;
   s->max_grid = ctx->sm_count * kCtasPerSm;
-  cudaError_t e = cudaMalloc((void**)&s->d_partials, (size_t)s->max_grid * kSlots * sizeof(float));
+  cudaError_t e = lin_opt_in_all();
+  if (e == cudaSuccess) e = cudaMalloc((void**)&s->d_partials, (size_t)s->max_grid * kSlots * sizeof(float));
   if (e == cudaSuccess) e = cudaMalloc((void**)&s->d_result, kSlots * sizeof(double));
   if (e == cudaSuccess) e = cudaMalloc((void**)&s->d_dev, sizeof(PicpDev));
   if (e == cudaSuccess) e = cudaMemsetAsync(s->d_dev, 0, sizeof(PicpDev), ctx->stream);
@@ -696,7 +937,7 @@ int vo_picp_set_correspondences_dev(vo_picp* s, const int32_t* d_pairs, int64_t 
   s->n_pad = n_pad > 0 ? n_pad : 4;
   s->n_pairs = n_pairs;
   if (n_pairs) {
-    const long long blocks = (n_pairs + 255) / 256;
+    const long long blocks = (n_pad + 255) / 256;
     picp_pack_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(reinterpret_cast<const int2*>(d_pairs), n_pairs,
                                                                s->d_world, s->n_world, s->d_image, s->n_image,
                                                                s->d_pk, s->n_pad, s->d_dev);
@@ -799,6 +1040,12 @@ int vo_picp_fetch_stats(vo_picp* s, vo_picp_stats* stats_out, int n_rounds) {
   }
   return VO_OK;
 }
+
+#ifdef VO_PROFILE_STAMPS
+int vo_debug_stamps(unsigned long long out[8]) {
+  return cudaMemcpyFromSymbol(out, g_stamps, sizeof(unsigned long long) * 8) == cudaSuccess ? 0 : 2;
+}
+#endif
 
 int vo_picp_one_round(vo_picp* s, float thr, float damping, int keep_outliers, vo_picp_stats* stats) {
   int st = vo_picp_enqueue_rounds(s, thr, damping, keep_outliers, 1);

@@ -95,6 +95,26 @@ def test_linearize_edge_values(ctx, oracle):
             s.close()
 
 
+def test_mask_on_threshold_knife_edge(ctx, oracle):
+    """Measurements placed so that chi lands within a few ulps of the kernel threshold for EVERY
+    correspondence: the inlier mask then depends on the last bit of the projection (the kernel's
+    hand-rolled reciprocal and pinhole shortcut must be bit-identical to the reference arithmetic)."""
+    fr = synth.picp_frame(n=150000, seed=77, outlier_frac=0.0, invalid_frac=0.0)
+    uv, _ = oracle.project_points(fr["K"], 480, 640, fr["pose0"], fr["world"], keep_indices=True)
+    rng = np.random.default_rng(3)
+    ang = rng.uniform(0, 2 * np.pi, len(uv))
+    r = 50.0 * (1 + rng.integers(-3, 4, len(uv)) * 2.0 ** -23)
+    fr["image"] = (uv + np.stack([r * np.cos(ang), r * np.sin(ang)], 1)).astype(np.float32)
+    s = _solver(ctx, fr)
+    lin = s.linearize(2500.0, False, want_status=True, n_pairs=len(uv))
+    ref = oracle.linearize(fr["K"], 480, 640, fr["pose0"], fr["world"], fr["image"], fr["pairs"], 2500.0, False,
+                           accum="f64")
+    assert np.array_equal(lin["status"], ref["status"])
+    frac_in = (ref["status"] == 1).mean()
+    assert 0.2 < frac_in < 0.8  # the threshold really cuts through the set
+    s.close()
+
+
 def test_empty_and_invalid_correspondences(ctx):
     vo = product()
     fr = synth.picp_frame(n=16, seed=1)
