@@ -81,6 +81,8 @@ _sig("vo_triangulate_dev", C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp)
 _sig("vo_essential_recover", C.c_int, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, C.POINTER(C.c_int))
 _sig("vo_anti_join", C.c_int, _vp, _vp, _i64, _vp, _i64, _vp, C.POINTER(_i64))
 
+from .sharding import N_TERMS, pack_terms, shard_bounds, shard_range, unpack_terms  # noqa: E402,F401
+
 MAX_ROUNDS = 64
 STATUS_SKIPPED, STATUS_INLIER, STATUS_OUTLIER = 0, 1, 2
 

@@ -23,6 +23,9 @@ import time
 
 import numpy as np
 
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -323,7 +326,7 @@ def bench_matching(args, ctx, vo, torch, dev, rank, world, barrier, max_over_ran
     """BASELINE config 4: 1M x 1M, D = 10, row blocks of A sharded over the ranks, B replicated, no collective."""
     n1 = n2 = 1 << 20
     A, B = synth.descriptors(n1, n2, seed=42)
-    lo, hi = rank * n1 // world, (rank + 1) * n1 // world
+    lo, hi = vo.shard_range(n1, world, rank)
     dA = torch.from_numpy(A[lo:hi]).to(dev)
     dB = torch.from_numpy(B).to(dev)
     rows = hi - lo
