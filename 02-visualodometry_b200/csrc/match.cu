@@ -21,6 +21,8 @@
 
 #include <float.h>
 
+#include <cub/device/device_radix_sort.cuh>
+
 namespace {
 
 constexpr int kMatchThreads = 128;
@@ -123,6 +125,186 @@ __global__ void __launch_bounds__(kMatchThreads) match_scan_kernel(
     o_second[o] = second;
     o_idx[o] = idx;
   }
+}
+
+// ---------------------------------------------------------------- D = 10 (the reference's descriptor size)
+// Packed f32x2 over COLUMN pairs: lane 0 of every packed op is column j, lane 1 is column j+1; the
+// query row sits in registers as broadcast pairs (a_k, a_k).  The tile is stored per column pair as
+// 20 floats in the order the Eigen redux consumes them: dims (0,4 | 2,6 | 1,5 | 3,7 | 8,9).
+//
+// Exact pruning: every term is >= 0 and float addition is monotone, so the partial sum
+//   lb = (x0 + x4) + (x2 + x6)            (the first half of Eigen's reduction tree, same rounding)
+// never exceeds the full distance d.  A column can only change (best, second, idx) when d < second,
+// hence when lb < second; if no lane of the warp has such a column the other 6 dimensions and the
+// update are skipped.  Results are bit-identical to the unpruned scan.
+typedef unsigned long long f2;
+__device__ __forceinline__ f2 pack2(float lo, float hi) {
+  f2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f2 add2(f2 a, f2 b) {
+  f2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f2 sub2(f2 a, f2 b) {
+  f2 d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
+  f2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+// (a-b)^2 with ONE rounding of the product. ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even
+// under --fmad=false (observed with CUDA 12.9), which would change the last bit of the distance; an
+// explicit fma with a +0 addend rounds exactly like the multiplication and cannot be fused again.
+__device__ __forceinline__ f2 sq2(f2 a, f2 b) {
+  const f2 d = sub2(a, b);
+  return fma2(d, d, 0ull);
+}
+
+constexpr int kPairFloats = 20;  // one column pair in shared memory
+__device__ __forceinline__ int dim_slot10(int k) {  // position of dimension k inside a pair record
+  const int order[10] = {0, 4, 1, 5, 2, 6, 3, 7, 8, 9};  // slot of dim k: dims stored as 0,4,2,6,1,5,3,7,8,9
+  // dims 0,4,2,6,1,5,3,7,8,9 occupy slots 0..9 -> inverse permutation
+  (void)order;
+  switch (k) {
+    case 0: return 0; case 4: return 1; case 2: return 2; case 6: return 3; case 1: return 4;
+    case 5: return 5; case 3: return 6; case 7: return 7; case 8: return 8; default: return 9;
+  }
+}
+
+__global__ void __launch_bounds__(kMatchThreads) match_scan10_kernel(
+    const float* __restrict__ A, long long row_begin, long long row_end, const float* __restrict__ B,
+    long long n2, long long split_size, const unsigned* __restrict__ row_order, float* __restrict__ o_best,
+    float* __restrict__ o_second, int* __restrict__ o_idx) {
+  constexpr int DIM = 10;
+  __shared__ __align__(16) float sB[(kTileRows / 2) * kPairFloats];
+  const long long rows = row_end - row_begin;
+  const long long slot = (long long)blockIdx.x * kMatchThreads + threadIdx.x;
+  const bool valid = slot < rows;
+  // row_order (optional): query rows sorted along a Morton curve of the lower-bound dimensions, so the
+  // 32 rows of a warp prune the same columns; results are written back at the original row
+  const long long r = (valid && row_order) ? (long long)row_order[slot] : slot;
+  f2 a[DIM];  // slot order
+#pragma unroll
+  for (int k = 0; k < DIM; ++k) {
+    const float v = valid ? __ldg(A + (row_begin + r) * DIM + k) : 0.f;
+    a[dim_slot10(k)] = pack2(v, v);
+  }
+  float best = FLT_MAX, second = FLT_MAX;
+  int idx = -1;
+  const long long j_lo = (long long)blockIdx.y * split_size;
+  const long long j_hi = (j_lo + split_size < n2) ? j_lo + split_size : n2;
+  for (long long j0 = j_lo; j0 < j_hi; j0 += kTileRows) {
+    const int cnt = (int)((j_hi - j0 < kTileRows) ? (j_hi - j0) : kTileRows);
+    const int n_pairs = (cnt + 1) >> 1;
+    __syncthreads();
+    for (int t = threadIdx.x; t < n_pairs * 2 * DIM; t += kMatchThreads) {
+      const int jj = t / DIM, k = t - jj * DIM;
+      // an odd tail gets a copy of the last real column: it can only tie, and ties never win (strict <)
+      const int src = (jj < cnt) ? jj : cnt - 1;
+      sB[(jj >> 1) * kPairFloats + dim_slot10(k) * 2 + (jj & 1)] = __ldg(B + (j0 + src) * DIM + k);
+    }
+    __syncthreads();
+#pragma unroll 2
+    for (int p = 0; p < n_pairs; ++p) {
+      const float4* rec = reinterpret_cast<const float4*>(sB + p * kPairFloats);
+      const float4 v0 = rec[0], v1 = rec[1];  // dims (0,4) and (2,6) of both columns
+      const f2 x0 = sq2(pack2(v0.x, v0.y), a[0]), x4 = sq2(pack2(v0.z, v0.w), a[1]);
+      const f2 x2 = sq2(pack2(v1.x, v1.y), a[2]), x6 = sq2(pack2(v1.z, v1.w), a[3]);
+      const f2 lb = add2(add2(x0, x4), add2(x2, x6));  // p0[0] + p0[2]
+      float lb0, lb1;
+      unpack2(lb, lb0, lb1);
+      if (!__any_sync(0xffffffffu, (lb0 < second) || (lb1 < second))) continue;
+      const float4 v2 = rec[2], v3 = rec[3], v4 = rec[4];
+      const f2 x1 = sq2(pack2(v2.x, v2.y), a[4]), x5 = sq2(pack2(v2.z, v2.w), a[5]);
+      const f2 x3 = sq2(pack2(v3.x, v3.y), a[6]), x7 = sq2(pack2(v3.z, v3.w), a[7]);
+      const f2 x8 = sq2(pack2(v4.x, v4.y), a[8]), x9 = sq2(pack2(v4.z, v4.w), a[9]);
+      f2 d = add2(lb, add2(add2(x1, x5), add2(x3, x7)));  // (p0[0]+p0[2]) + (p0[1]+p0[3])
+      d = add2(add2(d, x8), x9);
+      float d0, d1;
+      unpack2(d, d0, d1);
+      const int j = (int)(j0 + 2 * p);
+      update_best(d0, j, best, second, idx);
+      if (2 * p + 1 < cnt) update_best(d1, j + 1, best, second, idx);
+    }
+  }
+  if (valid) {
+    const long long o = (long long)blockIdx.y * rows + r;  // r = original row
+    o_best[o] = best;
+    o_second[o] = second;
+    o_idx[o] = idx;
+  }
+}
+
+// ---- query-row ordering for the pruned scan: 4 x 8-bit Morton key over dims 0,4,2,6 (the lower-bound dims)
+__device__ __forceinline__ unsigned ordered_u32(float f) {  // monotone float -> uint map
+  const unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float from_ordered_u32(unsigned u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+__global__ void match_minmax10_kernel(const float* __restrict__ A, long long row_begin, long long rows,
+                                      unsigned* __restrict__ mm /* [4] min, [4] max, ordered */) {
+  const int dims[4] = {0, 4, 2, 6};
+  unsigned lo[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu}, hi[4] = {0, 0, 0, 0};
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (long long)gridDim.x * blockDim.x)
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+      const float v = __ldg(A + (row_begin + r) * 10 + dims[d]);
+      if (v == v && fabsf(v) <= FLT_MAX) {  // NaN / inf do not stretch the key range
+        const unsigned u = ordered_u32(v);
+        lo[d] = min(lo[d], u);
+        hi[d] = max(hi[d], u);
+      }
+    }
+#pragma unroll
+  for (int d = 0; d < 4; ++d) {
+    for (int o = 16; o > 0; o >>= 1) {
+      lo[d] = min(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], o));
+      hi[d] = max(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicMin(&mm[d], lo[d]);
+      atomicMax(&mm[4 + d], hi[d]);
+    }
+  }
+}
+
+__device__ __forceinline__ unsigned spread8(unsigned v) {  // abcdefgh -> a000b000...h (every 4th bit)
+  v &= 0xffu;
+  v = (v | (v << 12)) & 0x000f000fu;
+  v = (v | (v << 6)) & 0x03030303u;
+  v = (v | (v << 3)) & 0x11111111u;
+  return v;
+}
+
+__global__ void match_keys10_kernel(const float* __restrict__ A, long long row_begin, long long rows,
+                                    const unsigned* __restrict__ mm, unsigned* __restrict__ keys,
+                                    unsigned* __restrict__ ids) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const int dims[4] = {0, 4, 2, 6};
+  unsigned key = 0;
+#pragma unroll
+  for (int d = 0; d < 4; ++d) {
+    const float lo = from_ordered_u32(mm[d]), hi = from_ordered_u32(mm[4 + d]);
+    const float v = __ldg(A + (row_begin + r) * 10 + dims[d]);
+    float q = (hi > lo) ? (v - lo) / (hi - lo) * 255.f : 0.f;
+    q = (q == q) ? fminf(fmaxf(q, 0.f), 255.f) : 0.f;
+    key |= spread8((unsigned)q) << d;
+  }
+  keys[r] = key;
+  ids[r] = (unsigned)r;
 }
 
 // merge the per-split triples in ascending split order (exact: comparisons only), apply the
@@ -274,12 +456,15 @@ __global__ void idjoin_probe_kernel(const int* __restrict__ idA, long long row_b
 
 template <int DIM>
 void launch_scan(dim3 grid, cudaStream_t st, const float* A, long long rb, long long re, const float* B,
-                 long long n2, long long split, float* ob, float* os, int* oi) {
-  match_scan_kernel<DIM><<<grid, kMatchThreads, 0, st>>>(A, rb, re, B, n2, split, ob, os, oi);
+                 long long n2, long long split, const unsigned* order, float* ob, float* os, int* oi) {
+  if (DIM == 10) match_scan10_kernel<<<grid, kMatchThreads, 0, st>>>(A, rb, re, B, n2, split, order, ob, os, oi);
+  else match_scan_kernel<DIM><<<grid, kMatchThreads, 0, st>>>(A, rb, re, B, n2, split, ob, os, oi);
 }
 
 typedef void (*scan_fn)(dim3, cudaStream_t, const float*, long long, long long, const float*, long long, long long,
-                        float*, float*, int*);
+                        const unsigned*, float*, float*, int*);
+
+constexpr long long kSortMinRows = 8192;  // below this the scan is latency-bound and the ordering does not pay
 
 scan_fn scan_for_dim(int dim) {
   switch (dim) {
@@ -351,6 +536,15 @@ int vo_match_dev(vo_ctx* ctx, const float* d_descA, int64_t n1, const float* d_d
   const size_t o_pi = carve((size_t)n_splits * rows * 4), o_idx = carve((size_t)rows * 4);
   const size_t o_flags = carve((size_t)rows), o_counts = carve((size_t)merge_blocks * 4);
   const size_t o_small = carve(64), o_table = carve((size_t)table_size * 8);
+  // optional Morton ordering of the query rows (D = 10 pruned scan)
+  const bool ordered = (dim == 10) && rows >= kSortMinRows && n2 > 0;
+  size_t sort_tmp_bytes = 0;
+  if (ordered)
+    cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp_bytes, (const unsigned*)nullptr, (unsigned*)nullptr,
+                                    (const unsigned*)nullptr, (unsigned*)nullptr, (int)rows, 0, 32, ctx->stream);
+  const size_t o_keys = carve(ordered ? (size_t)rows * 4 : 0), o_keys2 = carve(ordered ? (size_t)rows * 4 : 0);
+  const size_t o_ids = carve(ordered ? (size_t)rows * 4 : 0), o_order = carve(ordered ? (size_t)rows * 4 : 0);
+  const size_t o_mm = carve(64), o_sorttmp = carve(sort_tmp_bytes);
   char* base;
   st = vo_scratch(ctx, off, (void**)&base);
   if (st) return st;
@@ -366,9 +560,27 @@ int vo_match_dev(vo_ctx* ctx, const float* d_descA, int64_t n1, const float* d_d
   unsigned long long* table = (unsigned long long*)(base + o_table);
   VO_CUDA(ctx, cudaMemsetAsync(d_total, 0, 64, ctx->stream));
 
+  const unsigned* order = nullptr;
+  if (ordered) {
+    unsigned* keys = (unsigned*)(base + o_keys);
+    unsigned* keys2 = (unsigned*)(base + o_keys2);
+    unsigned* ids = (unsigned*)(base + o_ids);
+    unsigned* sorted_ids = (unsigned*)(base + o_order);
+    unsigned* mm = (unsigned*)(base + o_mm);
+    VO_CUDA(ctx, cudaMemsetAsync(mm, 0xFF, 16, ctx->stream));
+    VO_CUDA(ctx, cudaMemsetAsync(mm + 4, 0x00, 16, ctx->stream));
+    match_minmax10_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(d_descA, row_begin, rows, mm);
+    VO_CHECK_LAUNCH(ctx, "match_minmax10_kernel");
+    match_keys10_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, ctx->stream>>>(d_descA, row_begin, rows, mm, keys, ids);
+    VO_CHECK_LAUNCH(ctx, "match_keys10_kernel");
+    VO_CUDA(ctx, cub::DeviceRadixSort::SortPairs(base + o_sorttmp, sort_tmp_bytes, keys, keys2, ids, sorted_ids,
+                                                 (int)rows, 0, 32, ctx->stream));
+    ctx->launches += 4;  // CUB's histogram + onesweep passes
+    order = sorted_ids;
+  }
   scan_fn scan = scan_for_dim(dim);
   dim3 grid((unsigned)row_blocks, (unsigned)n_splits);
-  scan(grid, ctx->stream, d_descA, row_begin, row_end, d_descB, n2, split_size, pb, ps, pi);
+  scan(grid, ctx->stream, d_descA, row_begin, row_end, d_descB, n2, split_size, order, pb, ps, pi);
   VO_CHECK_LAUNCH(ctx, "match_scan_kernel");
   match_merge_kernel<<<(unsigned)merge_blocks, 256, 0, ctx->stream>>>(pb, ps, pi, rows, (int)n_splits, dist_thr,
                                                                       ratio_thr, d_best, d_second, idx, flags,
