@@ -54,6 +54,10 @@ _sig("vo_comm_unique_id", C.c_int, _vp)
 _sig("vo_ctx_comm_init", C.c_int, _vp, C.c_int, C.c_int, _vp)
 _sig("vo_ctx_comm_destroy", C.c_int, _vp)
 _sig("vo_ctx_comm_size", C.c_int, _vp)
+_sig("vo_ctx_peer_export", C.c_int, _vp, _vp)
+_sig("vo_ctx_peer_attach", C.c_int, _vp, C.c_int, C.c_int, _vp)
+_sig("vo_ctx_peer_detach", C.c_int, _vp)
+_sig("vo_ctx_peer_active", C.c_int, _vp)
 _sig("vo_pose_inverse", None, _vp, _vp)
 _sig("vo_pose_mul", None, _vp, _vp, _vp)
 _sig("vo_project_points", C.c_int, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _i64, C.c_int, _vp, C.POINTER(_i64),
@@ -184,6 +188,23 @@ class Context:
 
     def comm_destroy(self):
         _L.vo_ctx_comm_destroy(self._h)
+
+    # fused exchange over NVLink peer memory: export my mailbox handle, attach everybody's
+    def peer_export(self):
+        buf = np.zeros(64, np.uint8)
+        self._check(_L.vo_ctx_peer_export(self._h, _p(buf)), "vo_ctx_peer_export")
+        return buf
+
+    def peer_attach(self, n_ranks, rank, handles):
+        h = np.ascontiguousarray(handles, np.uint8).reshape(n_ranks * 64)
+        self._check(_L.vo_ctx_peer_attach(self._h, n_ranks, rank, _p(h)), "vo_ctx_peer_attach")
+
+    def peer_detach(self):
+        _L.vo_ctx_peer_detach(self._h)
+
+    @property
+    def peer_active(self):
+        return bool(_L.vo_ctx_peer_active(self._h))
 
     def picp(self):
         return Picp(self)

@@ -99,6 +99,63 @@ int vo_ctx_comm_destroy(vo_ctx* ctx) {
 
 int vo_ctx_comm_size(const vo_ctx* ctx) { return ctx ? ctx->n_ranks : 0; }
 
+// ---- fused exchange over peer memory (CUDA IPC handles; the caller moves the 64-byte handles around)
+int vo_ctx_peer_export(vo_ctx* ctx, uint8_t handle[VO_IPC_HANDLE_BYTES]) {
+  if (!ctx || !handle) return VO_ERR_INVALID;
+  static_assert(sizeof(cudaIpcMemHandle_t) == VO_IPC_HANDLE_BYTES, "CUDA IPC handle size");
+  int st = vo_ctx_activate(ctx);
+  if (st) return st;
+  if (!ctx->mailbox) {
+    VO_CUDA(ctx, cudaMalloc(&ctx->mailbox, sizeof(VoMailbox)));
+    VO_CUDA(ctx, cudaMemset(ctx->mailbox, 0, sizeof(VoMailbox)));
+  }
+  cudaIpcMemHandle_t h;
+  VO_CUDA(ctx, cudaIpcGetMemHandle(&h, ctx->mailbox));
+  memcpy(handle, &h, VO_IPC_HANDLE_BYTES);
+  return VO_OK;
+}
+
+int vo_ctx_peer_attach(vo_ctx* ctx, int n_ranks, int rank, const uint8_t* handles) {
+  if (!ctx || !handles || n_ranks < 1 || n_ranks > VO_MAX_PEERS || rank < 0 || rank >= n_ranks) return VO_ERR_INVALID;
+  if (!ctx->mailbox) return vo_set_error(ctx, VO_ERR_STATE, "vo_ctx_peer_attach", "export first");
+  if (ctx->peer_n) return vo_set_error(ctx, VO_ERR_STATE, "vo_ctx_peer_attach", "already attached");
+  int st = vo_ctx_activate(ctx);
+  if (st) return st;
+  for (int r = 0; r < n_ranks; ++r) {
+    if (r == rank) {
+      ctx->peer_mailbox[r] = ctx->mailbox;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles + (size_t)r * VO_IPC_HANDLE_BYTES, VO_IPC_HANDLE_BYTES);
+    cudaError_t e = cudaIpcOpenMemHandle(&ctx->peer_mailbox[r], h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      for (int q = 0; q < r; ++q)
+        if (q != rank && ctx->peer_mailbox[q]) cudaIpcCloseMemHandle(ctx->peer_mailbox[q]);
+      for (int q = 0; q < VO_MAX_PEERS; ++q) ctx->peer_mailbox[q] = nullptr;
+      cudaGetLastError();
+      return vo_set_error(ctx, VO_ERR_CUDA, "cudaIpcOpenMemHandle", cudaGetErrorString(e));
+    }
+  }
+  ctx->peer_n = n_ranks;
+  ctx->peer_rank = rank;
+  return VO_OK;
+}
+
+int vo_ctx_peer_detach(vo_ctx* ctx) {
+  if (!ctx) return VO_ERR_INVALID;
+  if (ctx->peer_n) {
+    cudaStreamSynchronize(ctx->stream);
+    for (int r = 0; r < ctx->peer_n; ++r)
+      if (r != ctx->peer_rank && ctx->peer_mailbox[r]) cudaIpcCloseMemHandle(ctx->peer_mailbox[r]);
+  }
+  for (int q = 0; q < VO_MAX_PEERS; ++q) ctx->peer_mailbox[q] = nullptr;
+  ctx->peer_n = 0;
+  return VO_OK;
+}
+
+int vo_ctx_peer_active(const vo_ctx* ctx) { return (ctx && ctx->peer_n > 1) ? 1 : 0; }
+
 }  // extern "C"
 
 int vo_comm_allreduce_f64(vo_ctx* ctx, double* d_buf, int n) {

@@ -66,7 +66,9 @@ int vo_ctx_destroy(vo_ctx* ctx) {
   if (!ctx) return VO_OK;
   cudaSetDevice(ctx->device);
   vo_ctx_comm_destroy(ctx);
+  vo_ctx_peer_detach(ctx);
   cudaStreamSynchronize(ctx->stream);
+  if (ctx->mailbox) cudaFree(ctx->mailbox);
   if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);

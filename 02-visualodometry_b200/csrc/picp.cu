@@ -89,6 +89,9 @@ struct LinArgs {
   double* result;
   unsigned char* status;
   int fuse_solve;
+  // fused multi-GPU exchange (peer_n > 1): every rank's mailbox, mine at index peer_rank
+  int peer_n, peer_rank;
+  VoMailbox* peers[VO_MAX_PEERS];
 };
 
 __device__ __forceinline__ float dot3_rn(float a0, float b0, float a1, float b1, float a2, float b2) {
@@ -449,6 +452,41 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
                : "memory");
 }
 
+// ------------------------------------------------------------------ fused all-reduce over NVLink peer memory
+// One warp. Lane c owns term c. Push my 32 terms into every rank's mailbox (mine included), publish a
+// flag with release semantics, wait for every rank's flag, then sum the slots in RANK order: all ranks
+// add the same numbers in the same order, so they solve bit-identical systems without a broadcast.
+// Mailboxes are double-buffered by round parity; a rank can reach round s+2 only after every rank has
+// published s+1, i.e. finished reading round s, so a parity buffer is never overwritten while in use.
+__device__ __forceinline__ double picp_peer_allreduce(const LinArgs& a, double mine, int lane) {
+  VoMailbox* me = a.peers[a.peer_rank];
+  const unsigned seq = *(volatile unsigned*)&me->seq + 1u;  // this round's sequence number (same on all ranks)
+  const int par = (int)(seq & 1u);
+  for (int p = 0; p < a.peer_n; ++p) a.peers[p]->slots[par][a.peer_rank][lane] = mine;  // 256 B per peer
+  __threadfence_system();
+  __syncwarp();
+  if (lane < a.peer_n) *(volatile unsigned*)&a.peers[lane]->flags[par][a.peer_rank] = seq;
+  double total = 0.0;
+  bool ok = true;
+  for (int q = 0; q < a.peer_n; ++q) {
+    long long spins = 0;
+    while (*(volatile unsigned*)&me->flags[par][q] != seq) {
+      if (++spins > (1ll << 24)) {  // ~5 s: a peer never launched its round; flag it instead of hanging the GPU
+        ok = false;
+        break;
+      }
+    }
+    __threadfence_system();
+    total += *(volatile double*)&me->slots[par][q][lane];
+  }
+  __syncwarp();
+  if (lane == 0) {
+    *(volatile unsigned*)&me->seq = seq;
+    if (!ok) me->timeout = 1u;
+  }
+  return total;
+}
+
 // ------------------------------------------------------------------ linearize + reduce
 // Tile ring: kStages x (5 planes x kTile floats) in shared memory, filled by one producer lane
 // with cp.async.bulk and consumed by 8 warps; tile t belongs to CTA (t mod gridDim.x) and quad
@@ -613,6 +651,7 @@ __global__ void __launch_bounds__(kLinThreads, kCtasPerSm) picp_linearize_kernel
   if (threadIdx.x < kSlots) {
     double v = 0.0;
     for (int w = 0; w < kWarps; ++w) v += s_fin[w][threadIdx.x];
+    if (a.peer_n > 1) v = picp_peer_allreduce(a, v, threadIdx.x);  // warp 0: all ranks' terms, rank order
     a.result[threadIdx.x] = v;
     s_fin[0][threadIdx.x] = v;
   }
@@ -755,6 +794,9 @@ int launch_linearize(vo_picp* s, float thr, float damping, bool keep, bool statu
   a.result = s->d_result;
   a.status = status ? s->d_status : nullptr;
   a.fuse_solve = fuse_solve ? 1 : 0;
+  a.peer_n = ctx->peer_n > 1 ? ctx->peer_n : 0;
+  a.peer_rank = ctx->peer_rank;
+  for (int p = 0; p < VO_MAX_PEERS; ++p) a.peers[p] = (VoMailbox*)ctx->peer_mailbox[p];
   const int grid = grid_for(s);
   if (keep) {
     if (status) launch_lin2<true, true>(s->pinhole, grid, ctx->stream, a);
@@ -770,7 +812,7 @@ int launch_linearize(vo_picp* s, float thr, float damping, bool keep, bool statu
 // one Gauss-Newton round on the stream (single GPU: 1 launch; with a communicator: 2 + all-reduce)
 int enqueue_round(vo_picp* s, float thr, float damping, bool keep) {
   vo_ctx* ctx = s->ctx;
-  const bool multi = ctx->nccl_comm != nullptr;
+  const bool multi = ctx->nccl_comm != nullptr && ctx->peer_n <= 1;  // the fused peer exchange replaces NCCL
   int st = launch_linearize(s, thr, damping, keep, false, !multi);
   if (st) return st;
   if (multi) {
@@ -982,8 +1024,10 @@ int vo_picp_linearize(vo_picp* s, float thr, int keep_outliers, float H[36], flo
   VO_CUDA(ctx, cudaMemsetAsync(&s->d_dev->stop, 0, sizeof(int), ctx->stream));
   st = launch_linearize(s, thr, 0.f, keep_outliers != 0, status != nullptr, false);
   if (st) return st;
-  st = vo_comm_allreduce_f64(ctx, s->d_result, kSlots);
-  if (st) return st;
+  if (ctx->peer_n <= 1) {  // (with peers attached the kernel has already exchanged the terms)
+    st = vo_comm_allreduce_f64(ctx, s->d_result, kSlots);
+    if (st) return st;
+  }
   void* h;
   st = vo_pinned(ctx, kSlots * sizeof(double), &h);
   if (st) return st;
@@ -1028,6 +1072,14 @@ int vo_picp_fetch_stats(vo_picp* s, vo_picp_stats* stats_out, int n_rounds) {
   int st = vo_ctx_activate(ctx);
   if (st) return st;
   if (n_rounds < 0 || n_rounds > VO_PICP_MAX_ROUNDS) return VO_ERR_INVALID;
+  if (ctx->peer_n > 1) {  // a fused exchange that gave up waiting for a peer invalidates the rounds
+    void* hp;
+    st = vo_pinned(ctx, 64, &hp);
+    if (st) return st;
+    VO_CUDA(ctx, cudaMemcpyAsync(hp, &((VoMailbox*)ctx->mailbox)->timeout, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+    VO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (*(unsigned*)hp) return vo_set_error(ctx, VO_ERR_STATE, "vo_picp_fetch_stats", "peer exchange timed out (ranks out of step)");
+  }
   if (stats_out && n_rounds) {
     void* h;
     st = vo_pinned(ctx, sizeof(vo_picp_stats) * VO_PICP_MAX_ROUNDS, &h);

@@ -27,6 +27,19 @@ struct vo_ctx {
   void* nccl_comm = nullptr;
   int n_ranks = 1;
   int rank = 0;
+  // fused peer exchange: my mailbox (device memory, IPC-exported) and the peers' mapped mailboxes
+  void* mailbox = nullptr;
+  void* peer_mailbox[VO_MAX_PEERS] = {nullptr};
+  int peer_n = 0;     // 0: not attached
+  int peer_rank = 0;
+};
+
+// mailbox layout: [2 parities][VO_MAX_PEERS ranks][32 doubles] + flags [2][VO_MAX_PEERS] + sequence counter
+struct VoMailbox {
+  double slots[2][VO_MAX_PEERS][32];
+  unsigned flags[2][VO_MAX_PEERS];
+  unsigned seq;       // rounds exchanged so far (advanced by the kernel)
+  unsigned timeout;   // set by a kernel whose wait for a peer expired
 };
 
 int vo_set_error(vo_ctx* ctx, int status, const char* what, const char* detail);

@@ -127,11 +127,11 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def workload_config(n):
+def workload_config(n, exchange="fused peer stores over NVLink inside the linearize kernel"):
     return {"workload": f"synthetic PICP frame, {C_PER_GPU} correspondences per GPU x {ROUNDS} Gauss-Newton rounds "
                         f"(BASELINE config 3 frame; thr {THR:g}, inlier rejection), identity correspondences",
             "correspondences_per_gpu": C_PER_GPU, "rounds": ROUNDS, "kernel_threshold": THR,
-            "parallelism": f"correspondence shards x{n}, 32-double all-reduce per round" if n > 1 else "1 GPU",
+            "parallelism": f"correspondence shards x{n}, 32-double all-reduce per round ({exchange})" if n > 1 else "1 GPU",
             "l2": "inputs 294 MB (packed stream 210 MB) per GPU > 126 MB L2: no flush between iterations"}
 
 
@@ -162,6 +162,20 @@ def run_cuda(args):
         uid = torch.from_numpy(vo.comm_unique_id() if rank == 0 else np.zeros(128, np.uint8)).to(dev)
         dist.broadcast(uid, 0)
         ctx.comm_init(world, rank, uid.cpu().numpy())
+        if not args.nccl_only:
+            # fused exchange: all-gather the 64-byte IPC handles of the per-rank mailboxes and map them
+            mine = torch.from_numpy(ctx.peer_export()).to(dev)
+            allh = [torch.zeros(64, dtype=torch.uint8, device=dev) for _ in range(world)]
+            dist.all_gather(allh, mine)
+            try:
+                ctx.peer_attach(world, rank, torch.stack(allh).cpu().numpy())
+            except vo.VoError as e:  # no peer access between these GPUs: stay on the NCCL all-reduce
+                if rank == 0:
+                    print(f"bench.py: peer attach failed ({e}); using ncclAllReduce", file=sys.stderr)
+            ok = torch.tensor([1 if ctx.peer_active else 0], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if not int(ok.item()):
+                ctx.peer_detach()
 
     def barrier():
         torch.cuda.synchronize()
@@ -284,7 +298,9 @@ def run_cuda(args):
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world),
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": workload_config(world, "fused peer stores over NVLink inside the linearize kernel"
+                                          if ctx.peer_active else "ncclAllReduce + solve kernel"),
                 "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
                 "final": {"inliers_last_round": int(stats[-1].num_inliers), "chi_inliers": float(stats[-1].chi_inliers),
                           "pose_err_vs_gt": float(np.abs(final_pose - fr["pose_gt"]).max())}}
@@ -295,6 +311,7 @@ def run_cuda(args):
     solver.close()
     solver2.close()
     if multi:
+        ctx.peer_detach()
         ctx.comm_destroy()
         dist.destroy_process_group()
     ctx.close()
@@ -386,6 +403,7 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--nccl-only", action="store_true", help="N>1: ncclAllReduce + solve kernel instead of the fused peer exchange")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cuda" else args.warmup
     if args.impl == "reference":

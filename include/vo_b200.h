@@ -79,6 +79,20 @@ int vo_ctx_comm_init(vo_ctx* ctx, int n_ranks, int rank, const uint8_t id[128]);
 int vo_ctx_comm_destroy(vo_ctx* ctx);
 int vo_ctx_comm_size(const vo_ctx* ctx);
 
+/* Fused exchange over NVLink peer memory (replaces the NCCL call + separate solve launch of a PICP round):
+ * every rank exports a 64-byte CUDA IPC handle of its mailbox, the caller all-gathers the handles
+ * (n_ranks * 64 bytes, rank order) and attaches them. The last CTA of the linearize kernel then
+ * stores its 32 terms into every peer's mailbox, waits for all ranks' flags and sums in rank order, so
+ * all ranks solve the identical system in the same launch. Ranks must issue their PICP rounds in the
+ * same order. At most VO_MAX_PEERS ranks of one node. */
+#define VO_MAX_PEERS 8
+#define VO_IPC_HANDLE_BYTES 64
+int vo_ctx_peer_export(vo_ctx* ctx, uint8_t handle[VO_IPC_HANDLE_BYTES]);
+int vo_ctx_peer_attach(vo_ctx* ctx, int n_ranks, int rank, const uint8_t* handles);
+int vo_ctx_peer_detach(vo_ctx* ctx);
+/* 1 when PICP rounds on this context use the fused peer exchange */
+int vo_ctx_peer_active(const vo_ctx* ctx);
+
 /* --------------------------------------------------------- Isometry helpers
  * Eigen::Isometry3f inverse / product as the callers use them on the host
  * (exec/icp_test.cpp:79,114,142; src/cam.cpp:78-81). Pure host arithmetic. */
