@@ -25,6 +25,24 @@ _i64 = C.c_int64
 _f = C.c_float
 
 
+class SeqParams(C.Structure):
+    _fields_ = [("K", C.c_float * 9), ("rows", C.c_int32), ("cols", C.c_int32), ("dist_thr", C.c_float),
+                ("ratio_thr", C.c_float), ("kernel_threshold", C.c_float), ("damping", C.c_float),
+                ("keep_outliers", C.c_int32), ("max_rounds", C.c_int32), ("rel_tol", C.c_float)]
+
+
+def seq_params(K, rows=480, cols=640, dist_thr=0.2, ratio_thr=0.8, kernel_threshold=3000.0, damping=1.0,
+               keep_outliers=False, max_rounds=50, rel_tol=1e-5):
+    """the constants of exec/icp_test.cpp / src/my_utilities.h as a vo_seq_params"""
+    p = SeqParams()
+    for i, v in enumerate(np.asarray(K, np.float32).reshape(9)):
+        p.K[i] = float(v)
+    p.rows, p.cols, p.dist_thr, p.ratio_thr = rows, cols, dist_thr, ratio_thr
+    p.kernel_threshold, p.damping, p.keep_outliers = kernel_threshold, damping, int(keep_outliers)
+    p.max_rounds, p.rel_tol = max_rounds, rel_tol
+    return p
+
+
 class Stats(C.Structure):
     _fields_ = [("chi_inliers", C.c_float), ("chi_outliers", C.c_float), ("num_inliers", C.c_int32),
                 ("num_outliers", C.c_int32)]
@@ -84,6 +102,10 @@ _sig("vo_triangulate", C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp)
 _sig("vo_triangulate_dev", C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp)
 _sig("vo_essential_recover", C.c_int, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, C.POINTER(C.c_int))
 _sig("vo_anti_join", C.c_int, _vp, _vp, _i64, _vp, _i64, _vp, C.POINTER(_i64))
+_sig("vo_seq_batch_run", C.c_int, _vp, C.POINTER(SeqParams), C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp,
+     _vp, _vp, _vp, _vp, _vp, _vp, _vp)
+_sig("vo_seq_batch_run_dev", C.c_int, _vp, C.POINTER(SeqParams), C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp,
+     _vp, _vp, _vp, _vp, _vp, _vp, _vp)
 
 from .sharding import N_TERMS, pack_terms, shard_bounds, shard_range, unpack_terms  # noqa: E402,F401
 
@@ -277,6 +299,29 @@ class Context:
         self._check(_L.vo_essential_recover(self._h, _p(_f32(K).reshape(9)), _p(x1), _p(x2), len(x1), _p(E), _p(R),
                                             _p(t), _p(mask), C.byref(good)), "vo_essential_recover")
         return E.reshape(3, 3), R.reshape(3, 3), t, mask[: len(x1)], good.value
+
+    # ---- batched independent sequences (BASELINE config 5)
+    def seq_batch_run(self, params, cnt, uv, desc, id_real, world_cap=1024):
+        """host arrays cnt[S,F], uv[S,F,P,2], desc[S,F,P,10], id_real[S,F,P] -> dict of host results"""
+        cnt = _i32(cnt)
+        S, F = cnt.shape
+        P = uv.shape[2]
+        uv, desc, id_real = _f32(uv), _f32(desc), _i32(id_real)
+        out = dict(poses=np.zeros((S, F, 3, 4), np.float32), world_xyz=np.zeros((S, world_cap, 3), np.float32),
+                   world_id=np.zeros((S, world_cap), np.int32), world_cnt=np.zeros(S, np.int32),
+                   rounds=np.zeros((S, F), np.int32), inliers=np.zeros((S, F, 2), np.int32), status=np.zeros(S, np.int32))
+        self._check(_L.vo_seq_batch_run(self._h, C.byref(params), S, F, P, world_cap, _p(cnt), _p(uv), _p(desc),
+                                        _p(id_real), _p(out["poses"]), _p(out["world_xyz"]), _p(out["world_id"]),
+                                        _p(out["world_cnt"]), _p(out["rounds"]), _p(out["inliers"]), _p(out["status"])),
+                    "vo_seq_batch_run")
+        return out
+
+    def seq_batch_run_dev(self, params, S, F, P, world_cap, d_cnt, d_uv, d_desc, d_id, d_poses, d_wxyz, d_wid, d_wcnt,
+                          d_rounds=None, d_inliers=None, d_status=None):
+        """raw device pointers; only enqueues on the context's stream"""
+        self._check(_L.vo_seq_batch_run_dev(self._h, C.byref(params), S, F, P, world_cap, _p(d_cnt), _p(d_uv), _p(d_desc),
+                                            _p(d_id), _p(d_poses), _p(d_wxyz), _p(d_wid), _p(d_wcnt), _p(d_rounds),
+                                            _p(d_inliers), _p(d_status)), "vo_seq_batch_run_dev")
 
     def anti_join(self, matched_id, cand_id):
         m = _i32(matched_id).ravel()

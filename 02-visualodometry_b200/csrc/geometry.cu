@@ -13,94 +13,12 @@
 // These are latency / FP64-issue bound, not HBM bound: one thread per correspondence, no shared
 // staging; small dense solves (9x9 eigen, 3x3 SVD) run on one thread between the data-parallel
 // passes so nothing returns to the host mid-pipeline.
-#include "vo_common.cuh"
+#include "vo_device.cuh"
 
 #include <float.h>
 #include <math.h>
 
 namespace {
-
-// ---------------------------------------------------------------- small dense LA (double)
-// One-sided (Hestenes) Jacobi SVD of an M x N matrix held in registers/local memory:
-// A <- U*Sigma (columns orthogonal), V accumulates right singular vectors, w = singular values
-// sorted descending.
-template <int M, int N>
-__device__ void jacobi_svd_dev(double (&A)[M][N], double (&V)[N][N], double (&w)[N]) {
-#pragma unroll
-  for (int i = 0; i < N; ++i)
-#pragma unroll
-    for (int j = 0; j < N; ++j) V[i][j] = (i == j) ? 1.0 : 0.0;
-  const double eps = 4 * DBL_EPSILON;
-  for (int sweep = 0; sweep < 80; ++sweep) {
-    bool changed = false;
-#pragma unroll
-    for (int i = 0; i < N - 1; ++i)
-#pragma unroll
-      for (int j = i + 1; j < N; ++j) {
-        double a = 0, b = 0, p = 0;
-#pragma unroll
-        for (int k = 0; k < M; ++k) {
-          a += A[k][i] * A[k][i];
-          b += A[k][j] * A[k][j];
-          p += A[k][i] * A[k][j];
-        }
-        if (fabs(p) <= eps * sqrt(a * b) || p == 0.0) continue;
-        changed = true;
-        const double zeta = (b - a) / (2 * p);
-        const double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1 + zeta * zeta));
-        const double c = 1 / sqrt(1 + t * t), s = c * t;
-#pragma unroll
-        for (int k = 0; k < M; ++k) {
-          const double x = A[k][i], y = A[k][j];
-          A[k][i] = c * x - s * y;
-          A[k][j] = s * x + c * y;
-        }
-#pragma unroll
-        for (int k = 0; k < N; ++k) {
-          const double x = V[k][i], y = V[k][j];
-          V[k][i] = c * x - s * y;
-          V[k][j] = s * x + c * y;
-        }
-      }
-    if (!changed) break;
-  }
-#pragma unroll
-  for (int i = 0; i < N; ++i) {
-    double s = 0;
-#pragma unroll
-    for (int k = 0; k < M; ++k) s += A[k][i] * A[k][i];
-    w[i] = sqrt(s);
-  }
-#pragma unroll
-  for (int i = 0; i < N - 1; ++i) {
-#pragma unroll
-    for (int k = i + 1; k < N; ++k) {
-      if (w[k] > w[i]) {  // exchange sort keeps everything in registers
-        double t = w[i]; w[i] = w[k]; w[k] = t;
-#pragma unroll
-        for (int r = 0; r < M; ++r) { t = A[r][i]; A[r][i] = A[r][k]; A[r][k] = t; }
-#pragma unroll
-        for (int r = 0; r < N; ++r) { t = V[r][i]; V[r][i] = V[r][k]; V[r][k] = t; }
-      }
-    }
-  }
-}
-
-// OpenCV DLT: rows x*P[2]-P[0], y*P[2]-P[1] per view; X = null vector of the 4x4 system
-__device__ __forceinline__ void dlt_point_dev(const double* __restrict__ P1, const double* __restrict__ P2,
-                                              double x1, double y1, double x2, double y2, double (&X)[4]) {
-  double A[4][4], V[4][4], w[4];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    A[0][k] = x1 * P1[8 + k] - P1[k];
-    A[1][k] = y1 * P1[8 + k] - P1[4 + k];
-    A[2][k] = x2 * P2[8 + k] - P2[k];
-    A[3][k] = y2 * P2[8 + k] - P2[4 + k];
-  }
-  jacobi_svd_dev<4, 4>(A, V, w);
-#pragma unroll
-  for (int k = 0; k < 4; ++k) X[k] = V[k][3];
-}
 
 struct ProjPair { double P1[12], P2[12]; };
 
@@ -110,17 +28,10 @@ __global__ void __launch_bounds__(128) triangulate_kernel(ProjPair pp, const flo
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float2 a = __ldg(x1 + i), b = __ldg(x2 + i);
-  double X[4];
-  dlt_point_dev(pp.P1, pp.P2, a.x, a.y, b.x, b.y, X);
-  const float X0 = (float)X[0], X1 = (float)X[1], X2 = (float)X[2], X3 = (float)X[3];
-  const float scale = (X3 != 0.f) ? __fdiv_rn(1.f, X3) : 1.f;  // convertPointsFromHomogeneous
-  xyz[3 * i] = __fmul_rn(X0, scale);
-  xyz[3 * i + 1] = __fmul_rn(X1, scale);
-  xyz[3 * i + 2] = __fmul_rn(X2, scale);
+  triangulate_point_dev(pp.P1, pp.P2, a.x, a.y, b.x, b.y, xyz + 3 * i);
 }
 
 // ---------------------------------------------------------------- essential: moments pass
-constexpr int kMom = 45;  // upper triangle of the 9x9 moment matrix sum r r^T
 constexpr int kEssThreads = 128;
 
 struct EssCam { double fx, fy, cx, cy; };
@@ -159,91 +70,6 @@ __global__ void __launch_bounds__(kEssThreads) essential_moments_kernel(EssCam c
   }
 }
 
-struct EssState {
-  double E[9];
-  double R1[9], R2[9], t[3];  // decomposeEssentialMat
-  double R[9], tt[3];         // recoverPose result
-  int good[4];
-  int pick;
-  int n_good;
-};
-
-__device__ void mm3_dev(const double* A, const double* B, double* C) {
-  for (int i = 0; i < 3; ++i)
-    for (int j = 0; j < 3; ++j) {
-      double s = 0;
-      for (int k = 0; k < 3; ++k) s += A[3 * i + k] * B[3 * k + j];
-      C[3 * i + j] = s;
-    }
-}
-
-__device__ double det3_dev(const double* M) {
-  return M[0] * (M[4] * M[8] - M[5] * M[7]) - M[1] * (M[3] * M[8] - M[5] * M[6]) + M[2] * (M[3] * M[7] - M[4] * M[6]);
-}
-
-// E = U diag(w) V^T with U completed to a full orthogonal basis
-__device__ void svd3_dev(const double* E, double* U, double* w, double* V) {
-  double A[3][3], Vm[3][3], ww[3];
-  for (int i = 0; i < 3; ++i)
-    for (int j = 0; j < 3; ++j) A[i][j] = E[3 * i + j];
-  jacobi_svd_dev<3, 3>(A, Vm, ww);
-  double u[3][3];
-  for (int j = 0; j < 2; ++j)
-    for (int k = 0; k < 3; ++k) u[j][k] = (ww[j] > 0) ? A[k][j] / ww[j] : 0.0;
-  u[2][0] = u[0][1] * u[1][2] - u[0][2] * u[1][1];
-  u[2][1] = u[0][2] * u[1][0] - u[0][0] * u[1][2];
-  u[2][2] = u[0][0] * u[1][1] - u[0][1] * u[1][0];
-  for (int j = 0; j < 3; ++j)
-    for (int k = 0; k < 3; ++k) {
-      U[3 * k + j] = u[j][k];
-      V[3 * k + j] = Vm[k][j];
-    }
-  for (int j = 0; j < 3; ++j) w[j] = ww[j];
-}
-
-// cyclic two-sided Jacobi on a symmetric 9x9 matrix; returns the eigenvector of the smallest eigenvalue
-__device__ void smallest_eigvec9(double (&S)[9][9], double (&vec)[9]) {
-  double V[9][9];
-  for (int i = 0; i < 9; ++i)
-    for (int j = 0; j < 9; ++j) V[i][j] = (i == j) ? 1.0 : 0.0;
-  for (int sweep = 0; sweep < 60; ++sweep) {
-    double off = 0, diag = 0;
-    for (int i = 0; i < 9; ++i) {
-      diag += S[i][i] * S[i][i];
-      for (int j = i + 1; j < 9; ++j) off += S[i][j] * S[i][j];
-    }
-    if (off <= 1e-32 * diag) break;
-    for (int p = 0; p < 8; ++p)
-      for (int q = p + 1; q < 9; ++q) {
-        const double apq = S[p][q];
-        if (apq == 0.0) continue;
-        const double theta = (S[q][q] - S[p][p]) / (2 * apq);
-        const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1));
-        const double c = 1 / sqrt(t * t + 1), s = t * c;
-        for (int k = 0; k < 9; ++k) {
-          const double x = S[k][p], y = S[k][q];
-          S[k][p] = c * x - s * y;
-          S[k][q] = s * x + c * y;
-        }
-        for (int k = 0; k < 9; ++k) {
-          const double x = S[p][k], y = S[q][k];
-          S[p][k] = c * x - s * y;
-          S[q][k] = s * x + c * y;
-        }
-        for (int k = 0; k < 9; ++k) {
-          const double x = V[k][p], y = V[k][q];
-          V[k][p] = c * x - s * y;
-          V[k][q] = s * x + c * y;
-        }
-      }
-  }
-  int best = 0;
-  for (int i = 1; i < 9; ++i)
-    if (S[i][i] < S[best][best]) best = i;
-  for (int k = 0; k < 9; ++k) vec[k] = V[k][best];
-}
-
-// partial moments -> normalised 8-point -> essential projection -> decomposeEssentialMat. One thread.
 __global__ void essential_solve_kernel(const double* __restrict__ partials, int n_blocks, EssState* st) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   double m[kMom];
@@ -252,77 +78,7 @@ __global__ void essential_solve_kernel(const double* __restrict__ partials, int 
     for (int b = 0; b < n_blocks; ++b) v += partials[(size_t)b * kMom + k];
     m[k] = v;
   }
-  double S[9][9];
-  {
-    int k = 0;
-    for (int u = 0; u < 9; ++u)
-      for (int v = u; v < 9; ++v, ++k) S[u][v] = S[v][u] = m[k];
-  }
-  // RMS-isotropic Hartley normalisation derived from the moments themselves:
-  // r = x2 (x) x1 with x = (x, y, 1): sums of x1 live in row 8 of S, second moments on the diagonal
-  const double n = S[8][8];
-  const double m1x = S[6][8] / n, m1y = S[7][8] / n, m2x = S[2][8] / n, m2y = S[5][8] / n;
-  const double v1 = (S[6][6] + S[7][7]) / n - (m1x * m1x + m1y * m1y);
-  const double v2 = (S[2][2] + S[5][5]) / n - (m2x * m2x + m2y * m2y);
-  const double s1 = sqrt(2.0 / v1), s2 = sqrt(2.0 / v2);
-  const double T1[9] = {s1, 0, -s1 * m1x, 0, s1, -s1 * m1y, 0, 0, 1};
-  const double T2[9] = {s2, 0, -s2 * m2x, 0, s2, -s2 * m2y, 0, 0, 1};
-  double Kr[9][9];  // T2 (x) T1
-  for (int a = 0; a < 3; ++a)
-    for (int b = 0; b < 3; ++b)
-      for (int c = 0; c < 3; ++c)
-        for (int d = 0; d < 3; ++d) Kr[3 * a + b][3 * c + d] = T2[3 * a + c] * T1[3 * b + d];
-  double tmp[9][9], Sh[9][9];
-  for (int i = 0; i < 9; ++i)
-    for (int j = 0; j < 9; ++j) {
-      double s = 0;
-      for (int k = 0; k < 9; ++k) s += Kr[i][k] * S[k][j];
-      tmp[i][j] = s;
-    }
-  for (int i = 0; i < 9; ++i)
-    for (int j = i; j < 9; ++j) {
-      double s = 0;
-      for (int k = 0; k < 9; ++k) s += tmp[i][k] * Kr[j][k];
-      Sh[i][j] = Sh[j][i] = s;
-    }
-  double f[9];
-  smallest_eigvec9(Sh, f);
-  // E0 = T2^T Fh T1
-  const double T2t[9] = {T2[0], T2[3], T2[6], T2[1], T2[4], T2[7], T2[2], T2[5], T2[8]};
-  double t9[9], E0[9];
-  mm3_dev(T2t, f, t9);
-  mm3_dev(t9, T1, E0);
-  double U[9], w[3], V[9];
-  svd3_dev(E0, U, w, V);
-  double E[9];
-  for (int i = 0; i < 3; ++i)
-    for (int j = 0; j < 3; ++j) E[3 * i + j] = U[3 * i] * V[3 * j] + U[3 * i + 1] * V[3 * j + 1];
-  int big = 0;
-  for (int k = 1; k < 9; ++k)
-    if (fabs(E[k]) > fabs(E[big])) big = k;
-  if (E[big] < 0)
-    for (int k = 0; k < 9; ++k) E[k] = -E[k];
-  for (int k = 0; k < 9; ++k) st->E[k] = E[k];
-  // decomposeEssentialMat
-  double Vt[9];
-  svd3_dev(E, U, w, V);
-  for (int i = 0; i < 3; ++i)
-    for (int j = 0; j < 3; ++j) Vt[3 * i + j] = V[3 * j + i];
-  if (det3_dev(U) < 0)
-    for (int k = 0; k < 9; ++k) U[k] = -U[k];
-  if (det3_dev(Vt) < 0)
-    for (int k = 0; k < 9; ++k) Vt[k] = -Vt[k];
-  const double Wm[9] = {0, 1, 0, -1, 0, 0, 0, 0, 1};
-  const double Wt[9] = {0, -1, 0, 1, 0, 0, 0, 0, 1};
-  double UW[9];
-  mm3_dev(U, Wm, UW);
-  mm3_dev(UW, Vt, st->R1);
-  mm3_dev(U, Wt, UW);
-  mm3_dev(UW, Vt, st->R2);
-  st->t[0] = U[2];
-  st->t[1] = U[5];
-  st->t[2] = U[8];
-  for (int c = 0; c < 4; ++c) st->good[c] = 0;
+  essential_from_moments(m, st);
 }
 
 // recoverPose's cheirality vote: each correspondence triangulated against the 4 candidates
@@ -338,33 +94,14 @@ __global__ void __launch_bounds__(128) essential_cheirality_kernel(EssCam cam, c
   if (threadIdx.x < 3) sT[threadIdx.x] = st->t[threadIdx.x];
   __syncthreads();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const double dist_thr = 50.0;
-  const double P0[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
   int ok[4] = {0, 0, 0, 0};
   if (i < n) {
     const float2 p = __ldg(x1 + i), q = __ldg(x2 + i);
     const double a0 = ((double)p.x - cam.cx) / cam.fx, a1 = ((double)p.y - cam.cy) / cam.fy;
     const double b0 = ((double)q.x - cam.cx) / cam.fx, b1 = ((double)q.y - cam.cy) / cam.fy;
     for (int c = 0; c < 4; ++c) {
-      const double* R = sR[c & 1];
-      const double sg = (c < 2) ? 1.0 : -1.0;
-      double P[12];
-#pragma unroll
-      for (int r = 0; r < 3; ++r) {
-        P[4 * r] = R[3 * r];
-        P[4 * r + 1] = R[3 * r + 1];
-        P[4 * r + 2] = R[3 * r + 2];
-        P[4 * r + 3] = sg * sT[r];
-      }
-      double Q[4];
-      dlt_point_dev(P0, P, a0, a1, b0, b1, Q);
-      bool good = Q[2] * Q[3] > 0;
-      const double q0 = Q[0] / Q[3], q1 = Q[1] / Q[3], q2 = Q[2] / Q[3];
-      good = good && (q2 < dist_thr);
-      const double z2 = P[8] * q0 + P[9] * q1 + P[10] * q2 + P[11];
-      good = good && (z2 > 0) && (z2 < dist_thr);
-      ok[c] = good;
-      masks[(size_t)c * n + i] = good ? 255 : 0;
+      ok[c] = cheirality_ok(sR[0], sR[1], sT, c, a0, a1, b0, b1);
+      masks[(size_t)c * n + i] = ok[c] ? 255 : 0;
     }
   }
   for (int c = 0; c < 4; ++c) {
@@ -376,11 +113,7 @@ __global__ void __launch_bounds__(128) essential_cheirality_kernel(EssCam cam, c
 __global__ void essential_pick_kernel(EssState* st) {
   if (threadIdx.x != 0) return;
   const int* g = st->good;
-  int pick;
-  if (g[0] >= g[1] && g[0] >= g[2] && g[0] >= g[3]) pick = 0;
-  else if (g[1] >= g[0] && g[1] >= g[2] && g[1] >= g[3]) pick = 1;
-  else if (g[2] >= g[0] && g[2] >= g[1] && g[2] >= g[3]) pick = 2;
-  else pick = 3;
+  const int pick = recover_pose_pick(g);
   const double* R = (pick & 1) ? st->R2 : st->R1;
   const double sg = (pick < 2) ? 1.0 : -1.0;
   for (int k = 0; k < 9; ++k) st->R[k] = R[k];
@@ -391,10 +124,6 @@ __global__ void essential_pick_kernel(EssState* st) {
 
 // ---------------------------------------------------------------- Camera::projectPoints
 struct ProjCam { float K[9]; float T[12]; float umax, vmax; };
-
-__device__ __forceinline__ float dot3_rn(float a0, float b0, float a1, float b1, float a2, float b2) {
-  return __fadd_rn(__fmul_rn(a0, b0), __fadd_rn(__fmul_rn(a1, b1), __fmul_rn(a2, b2)));
-}
 
 // camera.h:24-36 in the reference's float32 evaluation order (no FMA)
 __device__ __forceinline__ bool project_point_dev(const ProjCam& c, float px, float py, float pz, float& u, float& v) {

@@ -17,7 +17,7 @@
 // sub/mul/add in the order Eigen's SSE squaredNorm redux uses for VectorXf;
 // nothing is contracted to FMA, so indices and accept flags are bit-exact against the oracle.
 // This is FP32-issue bound (30 flop per pair, D = 10): no tensor cores, see DESIGN.md.
-#include "vo_common.cuh"
+#include "vo_device.cuh"
 
 #include <float.h>
 
@@ -28,57 +28,6 @@ namespace {
 constexpr int kMatchThreads = 128;
 constexpr int kTileRows = 256;  // rows of B per shared-memory tile
 constexpr int kMaxDim = 16;
-
-template <int DIM>
-__device__ __forceinline__ float sq_term(const float (&a)[DIM], const float* __restrict__ b, int k) {
-  const float d = __fsub_rn(a[k], b[k]);
-  return __fmul_rn(d, d);
-}
-
-// (a-b).squaredNorm() in Eigen's LinearVectorizedTraversal order with 4-wide packets
-template <int DIM>
-__device__ __forceinline__ float sqdist_eigen(const float (&a)[DIM], const float* __restrict__ b) {
-  if (DIM < 4) {
-    float r = sq_term<DIM>(a, b, 0);
-#pragma unroll
-    for (int k = 1; k < DIM; ++k) r = __fadd_rn(r, sq_term<DIM>(a, b, k));
-    return r;
-  }
-  constexpr int n4 = DIM / 4 * 4, n8 = DIM / 8 * 8;
-  float p0[4], p1[4];
-#pragma unroll
-  for (int l = 0; l < 4; ++l) p0[l] = sq_term<DIM>(a, b, l);
-  if (n4 > 4) {
-#pragma unroll
-    for (int l = 0; l < 4; ++l) p1[l] = sq_term<DIM>(a, b, 4 + l);
-#pragma unroll
-    for (int i = 8; i < n8; i += 8)
-#pragma unroll
-      for (int l = 0; l < 4; ++l) {
-        p0[l] = __fadd_rn(p0[l], sq_term<DIM>(a, b, i + l));
-        p1[l] = __fadd_rn(p1[l], sq_term<DIM>(a, b, i + 4 + l));
-      }
-#pragma unroll
-    for (int l = 0; l < 4; ++l) p0[l] = __fadd_rn(p0[l], p1[l]);
-    if (n4 > n8) {
-#pragma unroll
-      for (int l = 0; l < 4; ++l) p0[l] = __fadd_rn(p0[l], sq_term<DIM>(a, b, n8 + l));
-    }
-  }
-  float r = __fadd_rn(__fadd_rn(p0[0], p0[2]), __fadd_rn(p0[1], p0[3]));
-#pragma unroll
-  for (int k = n4; k < DIM; ++k) r = __fadd_rn(r, sq_term<DIM>(a, b, k));
-  return r;
-}
-
-// my_utilities.h:93-99
-__device__ __forceinline__ void update_best(float d, int j, float& best, float& second, int& idx) {
-  const bool lt = d < best;
-  const float s2 = (d < second) ? d : second;
-  second = lt ? best : s2;
-  idx = lt ? j : idx;
-  best = lt ? d : best;
-}
 
 template <int DIM>
 __global__ void __launch_bounds__(kMatchThreads) match_scan_kernel(

@@ -30,7 +30,7 @@
 // Rounding contract: everything that decides the inlier mask (camera point, projection,
 // reciprocal, error, chi) uses explicit round-to-nearest intrinsics in the reference's
 // evaluation order and is never contracted to FMA; J, H and b are tolerance-level and use FMA.
-#include "vo_common.cuh"
+#include "vo_device.cuh"
 
 #include <float.h>
 #include <math.h>
@@ -52,11 +52,6 @@ constexpr int kThreads = VO_LIN_THREADS;  // consumer threads per CTA of the lin
 constexpr int kWarps = kThreads / 32;
 constexpr int kSlots = 32;       // partial row: 0..20 H, 21..26 b, 27 chi_in, 28 chi_out, 29 n_in, 30 n_out
 constexpr int kCtasPerSm = VO_LIN_CTAS;
-
-struct PicpCam {
-  float K[9];
-  float umax, vmax;  // cols-1, rows-1 as float (camera.h:31-34 compares float against int)
-};
 
 struct PicpDev {
   float pose[12];
@@ -94,12 +89,6 @@ struct LinArgs {
   VoMailbox* peers[VO_MAX_PEERS];
 };
 
-__device__ __forceinline__ float dot3_rn(float a0, float b0, float a1, float b1, float a2, float b2) {
-  return __fadd_rn(__fmul_rn(a0, b0), __fadd_rn(__fmul_rn(a1, b1), __fmul_rn(a2, b2)));
-}
-
-__device__ __forceinline__ bool finite_f(float x) { return fabsf(x) <= FLT_MAX; }
-
 // ---- packed f32x2 arithmetic (sm_100a): one instruction, two IEEE round-to-nearest float ops.
 // The FP32 pipe retires the same lanes per clock either way; packing halves the issue slots, which
 // is what bounds this kernel (profiles/r01_picp_linearize_v1.md).
@@ -123,51 +112,6 @@ __device__ __forceinline__ f2 mul2(f2 a, f2 b) {
   return d;
 }
 __device__ __forceinline__ f2 neg2(f2 a) { return a ^ 0x8000000080000000ull; }
-
-// Exact projection, error and chi of ONE correspondence (camera.h:24-36, picp_solver.cpp:32-36,74):
-// every operation is an explicitly rounded float32 op in the reference's order, never contracted.
-// Straight-line on the common path so that the two points of a pair interleave in the pipeline.
-struct PointTerms {
-  float c0, c1, c2, q0, q1, iz, e0, e1, chi;
-  int st;
-};
-
-template <bool PINHOLE>
-__device__ __forceinline__ PointTerms picp_project(const PicpCam& cam, const float* __restrict__ T, float thr,
-                                                   float px, float py, float pz, float zu, float zv, bool valid) {
-  PointTerms t;
-  t.c0 = __fadd_rn(T[3], dot3_rn(T[0], px, T[1], py, T[2], pz));
-  t.c1 = __fadd_rn(T[7], dot3_rn(T[4], px, T[5], py, T[6], pz));
-  t.c2 = __fadd_rn(T[11], dot3_rn(T[8], px, T[9], py, T[10], pz));
-  // Shortcut (pinhole K = [fx 0 cx; 0 fy cy; 0 0 1], finite c0/c1, 1e-30 <= c2 <= 1e30):
-  //  * 0*c1 and 0*c0 are exact zeros, so q = (fx*c0 + cx*c2, fy*c1 + cy*c2, c2) bit for bit;
-  //  * rcp.approx + one Newton step on FMA is the correctly rounded 1/c2 for normal-range
-  //    operands (the sequence __frcp_rn itself runs once its range check has passed).
-  const bool shortcut = PINHOLE && (t.c2 >= 1e-30f) && (t.c2 <= 1e30f) && finite_f(t.c0) && finite_f(t.c1);
-  if (PINHOLE) {
-    t.q0 = __fadd_rn(__fmul_rn(cam.K[0], t.c0), __fmul_rn(cam.K[2], t.c2));
-    t.q1 = __fadd_rn(__fmul_rn(cam.K[4], t.c1), __fmul_rn(cam.K[5], t.c2));
-    float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t.c2));
-    t.iz = fmaf(r, fmaf(-t.c2, r, 1.f), r);
-  }
-  if (!shortcut && !(t.c2 <= 0.f)) {
-    // rare: the reference's arithmetic verbatim (general K, IEEE reciprocal)
-    t.q0 = dot3_rn(cam.K[0], t.c0, cam.K[1], t.c1, cam.K[2], t.c2);
-    t.q1 = dot3_rn(cam.K[3], t.c0, cam.K[4], t.c1, cam.K[5], t.c2);
-    t.iz = __frcp_rn(dot3_rn(cam.K[6], t.c0, cam.K[7], t.c1, cam.K[8], t.c2));  // == (float)(1./(double)q2)
-  }
-  const float u = __fmul_rn(t.q0, t.iz);
-  const float v = __fmul_rn(t.q1, t.iz);
-  // camera.h:27,31-34 with their NaN behaviour: a NaN compares false and stays "inside"
-  // (`valid` is false only for the padding lanes of the last quad of the stream)
-  const bool inside = valid && !(t.c2 <= 0.f) && !(u < 0.f) && !(u > cam.umax) && !(v < 0.f) && !(v > cam.vmax);
-  t.e0 = __fsub_rn(u, zu);
-  t.e1 = __fsub_rn(v, zv);
-  t.chi = __fadd_rn(__fmul_rn(t.e0, t.e0), __fmul_rn(t.e1, t.e1));
-  t.st = inside ? ((t.chi > thr) ? VO_PICP_OUTLIER : VO_PICP_INLIER) : VO_PICP_SKIPPED;
-  return t;
-}
 
 // Two correspondences: exact part per point, then J, H += lambda J^T J and b += lambda J^T e in packed
 // f32x2 (lane 0 = first point, lane 1 = second; acc2[k] holds the two lanes' partial sums of slot k).
@@ -249,146 +193,18 @@ __device__ __forceinline__ void picp_pair(const PicpCam& cam, const float* __res
   }
 }
 
-// ------------------------------------------------------------------ 6x6 solve + pose update
-// Eigen::LDLT<Matrix6f> (diagonal pivoting) restated for one thread, float32
-// (picp_solver.cpp:102), then v2tEuler(dx)*pose (defs.h:100-136, picp_solver.cpp:103).
-__device__ void ldlt_solve6_dev(float (&m)[6][6], float (&d)[6]) {
-  int tr[6];
-  for (int k = 0; k < 6; ++k) {
-    int big = k;
-    float bigv = fabsf(m[k][k]);
-    for (int i = k + 1; i < 6; ++i)
-      if (fabsf(m[i][i]) > bigv) {
-        bigv = fabsf(m[i][i]);
-        big = i;
-      }
-    tr[k] = big;
-    if (big != k) {
-      for (int j = 0; j < k; ++j) { float t = m[k][j]; m[k][j] = m[big][j]; m[big][j] = t; }
-      for (int i = big + 1; i < 6; ++i) { float t = m[i][k]; m[i][k] = m[i][big]; m[i][big] = t; }
-      { float t = m[k][k]; m[k][k] = m[big][big]; m[big][big] = t; }
-      for (int i = k + 1; i < big; ++i) { float t = m[i][k]; m[i][k] = m[big][i]; m[big][i] = t; }
-    }
-    if (k > 0) {
-      float temp[6];
-      float s = 0.f;
-      for (int j = 0; j < k; ++j) {
-        temp[j] = __fmul_rn(m[j][j], m[k][j]);
-        s = __fadd_rn(s, __fmul_rn(m[k][j], temp[j]));
-      }
-      m[k][k] = __fsub_rn(m[k][k], s);
-      for (int i = k + 1; i < 6; ++i) {
-        float a = 0.f;
-        for (int j = 0; j < k; ++j) a = __fadd_rn(a, __fmul_rn(m[i][j], temp[j]));
-        m[i][k] = __fsub_rn(m[i][k], a);
-      }
-    }
-    const float akk = m[k][k];
-    const bool valid = fabsf(akk) > 0.f;
-    if (k == 0 && !valid) {
-      for (int j = 0; j < 6; ++j) tr[j] = j;
-      break;
-    }
-    if (valid)
-      for (int i = k + 1; i < 6; ++i) m[i][k] = __fdiv_rn(m[i][k], akk);
-  }
-  for (int k = 0; k < 6; ++k) { float t = d[k]; d[k] = d[tr[k]]; d[tr[k]] = t; }
-  for (int i = 0; i < 6; ++i)
-    for (int j = 0; j < i; ++j) d[i] = __fsub_rn(d[i], __fmul_rn(m[i][j], d[j]));
-  for (int i = 0; i < 6; ++i) d[i] = (fabsf(m[i][i]) > FLT_MIN) ? __fdiv_rn(d[i], m[i][i]) : 0.f;
-  for (int i = 5; i >= 0; --i)
-    for (int j = i + 1; j < 6; ++j) d[i] = __fsub_rn(d[i], __fmul_rn(m[j][i], d[j]));
-  for (int k = 5; k >= 0; --k) { float t = d[k]; d[k] = d[tr[k]]; d[tr[k]] = t; }
-}
-
-__device__ void mat3_mul_rn(const float* A, const float* B, float* C) {
-  for (int i = 0; i < 3; ++i)
-    for (int j = 0; j < 3; ++j)
-      C[3 * i + j] = dot3_rn(A[3 * i], B[j], A[3 * i + 1], B[3 + j], A[3 * i + 2], B[6 + j]);
-}
-
-// Unpivoted LDL^T of a symmetric positive definite 6x6, fully unrolled so that every entry lives in
-// a register.  H + damping*I with damping > 0 is SPD (H is a sum of J^T J), so diagonal pivoting is
-// not needed for stability; the result differs from Eigen's pivoted LDLT by float rounding only
-// (covered by the 1e-5 pose tolerance).  damping <= 0 keeps the pivoted restatement above.
-__device__ __forceinline__ void ldl_solve6_spd(float (&m)[6][6], float (&d)[6]) {
-  float D[6];
-#pragma unroll
-  for (int j = 0; j < 6; ++j) {
-    float t[6];
-    float dj = m[j][j];
-#pragma unroll
-    for (int k = 0; k < 6; ++k)
-      if (k < j) {
-        t[k] = m[j][k] * D[k];
-        dj = fmaf(-m[j][k], t[k], dj);
-      }
-    D[j] = dj;
-    const float inv = __fdiv_rn(1.f, dj);
-#pragma unroll
-    for (int i = 0; i < 6; ++i)
-      if (i > j) {
-        float v = m[i][j];
-#pragma unroll
-        for (int k = 0; k < 6; ++k)
-          if (k < j) v = fmaf(-m[i][k], t[k], v);
-        m[i][j] = v * inv;
-      }
-  }
-#pragma unroll
-  for (int i = 0; i < 6; ++i)
-#pragma unroll
-    for (int j = 0; j < 6; ++j)
-      if (j < i) d[i] = fmaf(-m[i][j], d[j], d[i]);
-#pragma unroll
-  for (int i = 0; i < 6; ++i) d[i] = __fdiv_rn(d[i], D[i]);
-#pragma unroll
-  for (int i = 5; i >= 0; --i)
-#pragma unroll
-    for (int j = 0; j < 6; ++j)
-      if (j > i) d[i] = fmaf(-m[j][i], d[j], d[i]);
-}
-
 // result[32] (double) -> damped solve -> pose update, stats ring, convergence flag. One thread.
 __device__ void picp_solve_update(const double* __restrict__ res, float damping, PicpDev* dev) {
-  float m[6][6], rhs[6];
-  {
-    int k = 0;
+  float Hu[21], bb[6], pose[12];
 #pragma unroll
-    for (int i = 0; i < 6; ++i)
+  for (int k = 0; k < 21; ++k) Hu[k] = (float)res[k];
 #pragma unroll
-      for (int j = 0; j < 6; ++j)
-        if (j >= i) {
-          const float h = (float)res[k++];
-          m[i][j] = h;
-          m[j][i] = h;
-        }
-  }
+  for (int k = 0; k < 6; ++k) bb[k] = (float)res[21 + k];
 #pragma unroll
-  for (int i = 0; i < 6; ++i) {
-    m[i][i] = __fadd_rn(m[i][i], damping);  // H += I*damping (picp_solver.cpp:96)
-    rhs[i] = -(float)res[21 + i];
-  }
-  if (damping > 0.f) ldl_solve6_spd(m, rhs);
-  else ldlt_solve6_dev(m, rhs);
-  // Rx(dx3) Ry(dx4) Rz(dx5) (defs.h:100-136); sinf/cosf are within 2 ulp of libm's
-  float sx, cx, sy, cy, sz, cz;
-  sincosf(rhs[3], &sx, &cx);
-  sincosf(rhs[4], &sy, &cy);
-  sincosf(rhs[5], &sz, &cz);
-  const float Rx[9] = {1, 0, 0, 0, cx, -sx, 0, sx, cx};
-  const float Ry[9] = {cy, 0, sy, 0, 1, 0, -sy, 0, cy};
-  const float Rz[9] = {cz, -sz, 0, sz, cz, 0, 0, 0, 1};
-  float Rxy[9], Rd[9], T[12], out[12];
-  mat3_mul_rn(Rx, Ry, Rxy);
-  mat3_mul_rn(Rxy, Rz, Rd);
-  for (int i = 0; i < 12; ++i) T[i] = dev->pose[i];
-  for (int i = 0; i < 3; ++i) {
-    for (int j = 0; j < 4; ++j)
-      out[4 * i + j] = dot3_rn(Rd[3 * i], T[j], Rd[3 * i + 1], T[4 + j], Rd[3 * i + 2], T[8 + j]);
-    out[4 * i + 3] = __fadd_rn(out[4 * i + 3], rhs[i]);
-  }
-  for (int i = 0; i < 12; ++i) dev->pose[i] = out[i];
+  for (int i = 0; i < 12; ++i) pose[i] = dev->pose[i];
+  picp_gn_step(Hu, bb, damping, pose);
+#pragma unroll
+  for (int i = 0; i < 12; ++i) dev->pose[i] = pose[i];
   const int r = dev->round;
   vo_picp_stats st;
   st.chi_inliers = (float)res[27];

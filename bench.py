@@ -288,6 +288,7 @@ def run_cuda(args):
     extra = {}
     if not args.no_extras:
         extra.update(bench_matching(args, ctx, vo, torch, dev, rank, world, barrier, max_over_ranks))
+        extra.update(bench_sequences(args, ctx, vo, torch, dev, stream, rank, world, barrier, max_over_ranks))
         if not multi:
             extra.update(bench_small_frame(args, ctx, torch, dev, stream))
 
@@ -368,6 +369,89 @@ def bench_matching(args, ctx, vo, torch, dev, rank, world, barrier, max_over_ran
                          "bound": "fp32 lanes: 29 unfused sub/mul/add per pair for bit-exact rounding; the exact "
                                   "lower-bound pruning (first 4 dims of the Eigen reduction tree, Morton-ordered query "
                                   "rows) skips the other 18 when no lane of the warp can improve, so >1.0 is possible"}}
+
+
+def simulate_sequences_torch(torch, dev, n_seq, n_frames, seed, max_pts=128, chunk=256):
+    """tests/simulator.py vectorised over sequences on the GPU (torch is only the data generator here):
+    1000 landmarks U(-10,10)^2 x U(0,2), U(-1,1)^10 descriptors, 0.2-unit steps, the camera of data/camera.dat."""
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    cnt = torch.zeros((n_seq, n_frames), dtype=torch.int32, device=dev)
+    uv = torch.zeros((n_seq, n_frames, max_pts, 2), dtype=torch.float32, device=dev)
+    desc = torch.zeros((n_seq, n_frames, max_pts, 10), dtype=torch.float32, device=dev)
+    ids = torch.full((n_seq, n_frames, max_pts), -1, dtype=torch.int32, device=dev)
+    L = 1000
+    for s0 in range(0, n_seq, chunk):
+        S = min(chunk, n_seq - s0)
+        lm = torch.rand((S, L, 3), generator=g, device=dev, dtype=torch.float64)
+        lm = torch.stack([lm[..., 0] * 20 - 10, lm[..., 1] * 20 - 10, lm[..., 2] * 2], -1)
+        ld = (torch.rand((S, L, 10), generator=g, device=dev) * 2 - 1).float()
+        om = torch.cumsum(torch.randn((S, n_frames), generator=g, device=dev, dtype=torch.float64) * 0.01, 1) * 0.3
+        om[:, :2] = 0
+        om = om.clamp(-0.08, 0.08)
+        th = torch.cumsum(om, 1)                      # heading AFTER the turn of frame f
+        th0 = torch.cat([torch.zeros((S, 1), device=dev, dtype=torch.float64), th[:, :-1]], 1)
+        x = torch.cat([torch.zeros((S, 1), device=dev, dtype=torch.float64), torch.cumsum(0.2 * torch.cos(th), 1)[:, :-1]], 1)
+        y = torch.cat([torch.zeros((S, 1), device=dev, dtype=torch.float64), torch.cumsum(0.2 * torch.sin(th), 1)[:, :-1]], 1)
+        c, sn = torch.cos(th0), torch.sin(th0)
+        dx = lm[:, None, :, 0] - x[:, :, None]
+        dy = lm[:, None, :, 1] - y[:, :, None]
+        rx = c[:, :, None] * dx + sn[:, :, None] * dy          # robot frame
+        ry = -sn[:, :, None] * dx + c[:, :, None] * dy
+        rz = lm[:, None, :, 2].expand_as(rx)
+        zc = rx - 0.2                                           # camera frame: z forward, x right, y down
+        xc, yc = -ry, -rz
+        u = 180.0 * xc / zc + 320.0
+        v = 180.0 * yc / zc + 240.0
+        vis = (zc > 0) & (zc < 5) & (u >= 0) & (u < 640) & (v >= 0) & (v < 480)
+        rank = torch.cumsum(vis.int(), 2) - 1
+        keep = vis & (rank < max_pts)
+        si, fi, li = torch.nonzero(keep, as_tuple=True)
+        slot = rank[si, fi, li].long()
+        cnt[s0:s0 + S] = keep.sum(2).int()
+        uv[s0 + si, fi, slot, 0] = u[si, fi, li].float()
+        uv[s0 + si, fi, slot, 1] = v[si, fi, li].float()
+        desc[s0 + si, fi, slot] = ld[si, li]
+        ids[s0 + si, fi, slot] = li.int()
+    return cnt, uv, desc, ids
+
+
+def bench_sequences(args, ctx, vo, torch, dev, stream, rank, world, barrier, max_over_ranks):
+    """BASELINE config 5: 4096 independent 121-frame sequences (full exec/icp_test.cpp loop per sequence),
+    sequences sharded over the ranks, no communication."""
+    total, F, P, W = 4096, 121, 128, 1024
+    lo, hi = vo.shard_range(total, world, rank)
+    S = hi - lo
+    cnt, uv, desc, ids = simulate_sequences_torch(torch, dev, S, F, seed=42 + rank)
+    poses = torch.empty((S, F, 12), dtype=torch.float32, device=dev)
+    wxyz = torch.empty((S, W, 3), dtype=torch.float32, device=dev)
+    wid = torch.empty((S, W), dtype=torch.int32, device=dev)
+    wcnt = torch.empty(S, dtype=torch.int32, device=dev)
+    status = torch.empty(S, dtype=torch.int32, device=dev)
+    rounds = torch.empty((S, F), dtype=torch.int32, device=dev)
+    params = vo.seq_params(synth.K_REF)
+
+    def run():
+        ctx.seq_batch_run_dev(params, S, F, P, W, cnt.data_ptr(), uv.data_ptr(), desc.data_ptr(), ids.data_ptr(),
+                              poses.data_ptr(), wxyz.data_ptr(), wid.data_ptr(), wcnt.data_ptr(), rounds.data_ptr(), None,
+                              status.data_ptr())
+
+    run()
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    steps = 3
+    a.record(stream)
+    for _ in range(steps):
+        run()
+    b.record(stream)
+    barrier()
+    ms = max_over_ranks(a.elapsed_time(b)) / steps
+    ok = int((status == 0).sum().item())
+    return {"sequences": {"metric": "sequences_per_s", "value": total / (ms * 1e-3), "frames_per_s": total * F / (ms * 1e-3),
+                          "unit": "sequences/s", "ms_per_batch": ms, "n_sequences": total, "n_frames": F,
+                          "sequences_per_gpu": S, "ok_rank0": ok, "mean_rounds_per_frame": float(rounds[:, 1:].float().mean().item()),
+                          "mean_world_points": float(wcnt.float().mean().item()),
+                          "note": "one CTA per sequence runs the whole icp_test loop on the device; latency / issue bound"}}
 
 
 def bench_small_frame(args, ctx, torch, dev, stream):

@@ -184,6 +184,35 @@ int vo_essential_recover(vo_ctx* ctx, const float K[9], const float* x1, const f
 int vo_anti_join(vo_ctx* ctx, const int32_t* matched_id, int64_t n_matched,
                  const int32_t* cand_id, int64_t n_cand, uint8_t* keep, int64_t* n_keep);
 
+/* ------------------------------------------------------- batched independent sequences
+ * BASELINE config 5: n_seq independent sequences, each run through the reference's final pipeline
+ * (exec/icp_test.cpp:40-136: match(0,1) -> essential -> triangulate, then per frame match vs map, PICP
+ * with the driver's convergence loop, match vs previous frame, anti-join, triangulate, append) by ONE CTA
+ * without returning to the host; the map of every sequence stays in HBM. Layouts (S sequences, F frames,
+ * P = max_pts <= 128 points per frame, W = world_cap):
+ *   cnt[S][F]  uv[S][F][P][2]  desc[S][F][P][10]  id_real[S][F][P]      (id_meas = index inside the frame)
+ *   poses[S][F][12] camera-in-world (frame 0 = identity)   world_xyz[S][W][3]  world_id[S][W]  world_cnt[S]
+ *   rounds[S][F] (nullable)  inliers[S][F][2] = (inliers of the last round, correspondences) (nullable)
+ *   status[S]: 0 ok, 1 map capacity reached (overflow dropped), 2 fewer than 8 initial matches (nothing done) */
+typedef struct vo_seq_params {
+  float K[9];
+  int32_t rows, cols;
+  float dist_thr, ratio_thr;  /* my_utilities.h:44-46: 0.2, 0.8 */
+  float kernel_threshold;     /* icp_test.cpp:86: 3000 */
+  float damping;              /* picp_solver.cpp:11: 1 */
+  int32_t keep_outliers;      /* icp_test.cpp:95: 0 */
+  int32_t max_rounds;         /* icp_test.cpp:88: 50 */
+  float rel_tol;              /* icp_test.cpp:91: 1e-5 */
+} vo_seq_params;
+int vo_seq_batch_run(vo_ctx* ctx, const vo_seq_params* params, int n_seq, int n_frames, int max_pts, int world_cap,
+                     const int32_t* cnt, const float* uv, const float* desc, const int32_t* id_real,
+                     float* poses, float* world_xyz, int32_t* world_id, int32_t* world_cnt,
+                     int32_t* rounds, int32_t* inliers, int32_t* status);
+int vo_seq_batch_run_dev(vo_ctx* ctx, const vo_seq_params* params, int n_seq, int n_frames, int max_pts, int world_cap,
+                         const int32_t* d_cnt, const float* d_uv, const float* d_desc, const int32_t* d_id_real,
+                         float* d_poses, float* d_world_xyz, int32_t* d_world_id, int32_t* d_world_cnt,
+                         int32_t* d_rounds, int32_t* d_inliers, int32_t* d_status);
+
 #ifdef __cplusplus
 }
 #endif
