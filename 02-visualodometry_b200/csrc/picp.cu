@@ -314,7 +314,11 @@ constexpr size_t kLinSmemBytes = (size_t)kStages * 5 * kTile * sizeof(float);
 
 template <bool KEEP, bool STATUS, bool PINHOLE>
 __global__ void __launch_bounds__(kLinThreads, kCtasPerSm) picp_linearize_kernel(const LinArgs a) {
-  if (a.dev->stop) return;  // a converged device-side loop turns the remaining launches into no-ops
+  // Programmatic dependent launch: the next round's grid may start launching right away; its CTAs run this
+  // prologue (barrier init, first TMA tiles: the packed planes do not change between rounds) on the SMs this
+  // grid has already left, i.e. under the solve tail, and block in griddepcontrol.wait until this grid has
+  // completed and its pose / partials / ticket are visible.  Both instructions are no-ops in a normal launch.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (blockIdx.x == 0 && threadIdx.x == 0) VO_STAMP(0);
   extern __shared__ __align__(128) float s_tiles[];
   __shared__ __align__(8) unsigned long long s_full[kStages], s_empty[kStages];
@@ -323,7 +327,6 @@ __global__ void __launch_bounds__(kLinThreads, kCtasPerSm) picp_linearize_kernel
   __shared__ double s_fin[kWarps][kSlots];
   __shared__ int s_last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x < 12) s_pose[threadIdx.x] = a.dev->pose[threadIdx.x];
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int s = 0; s < kStages; ++s) {
@@ -343,11 +346,8 @@ __global__ void __launch_bounds__(kLinThreads, kCtasPerSm) picp_linearize_kernel
   if (warp == kWarps) {
     // ---------------- producer: one elected lane keeps the ring full
     if (lane == 0) {
-      int it = 0;
-      for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+      auto issue = [&](long long t, int it) {
         const int stage = it % kStages;
-        const unsigned phase = (unsigned)(it / kStages) & 1u;
-        mbar_wait_relaxed(&s_empty[stage], phase ^ 1u);
         const long long first = t * kTile;
         const long long left = ((a.n + 3) & ~3ll) - first;
         const unsigned bytes = (unsigned)((left < kTile ? left : kTile) * sizeof(float));
@@ -355,9 +355,32 @@ __global__ void __launch_bounds__(kLinThreads, kCtasPerSm) picp_linearize_kernel
         mbar_arrive_expect_tx(&s_full[stage], 5u * bytes);
 #pragma unroll
         for (int p = 0; p < 5; ++p) bulk_g2s(dst + p * kTile, a.pk + p * a.stride + first, bytes, &s_full[stage]);
+      };
+      // the first kStages tiles do not depend on the previous round: fetch them before the dependency resolves
+      int it = 0;
+      long long t = blockIdx.x;
+      for (; t < n_tiles && it < kStages; t += gridDim.x, ++it) issue(t, it);
+      asm volatile("griddepcontrol.wait;" ::: "memory");
+      if (*(volatile int*)&a.dev->stop) {
+        // converged device-side loop: this launch is a no-op, but the copies in flight must land before exit
+        for (int k = 0; k < it; ++k) mbar_wait(&s_full[k], 0u);
+        return;
       }
+      for (; t < n_tiles; t += gridDim.x, ++it) {
+        const int stage = it % kStages;
+        const unsigned phase = (unsigned)(it / kStages) & 1u;
+        mbar_wait_relaxed(&s_empty[stage], phase ^ 1u);
+        issue(t, it);
+      }
+    } else {
+      asm volatile("griddepcontrol.wait;" ::: "memory");
+      if (*(volatile int*)&a.dev->stop) return;
     }
   } else {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (*(volatile int*)&a.dev->stop) return;  // a converged device-side loop turns the remaining launches into no-ops
+    if (threadIdx.x < 12) s_pose[threadIdx.x] = a.dev->pose[threadIdx.x];
+    asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory");  // consumers only
     // ---------------- consumers
     float T[12];
 #pragma unroll
@@ -590,10 +613,25 @@ int grid_for(const vo_picp* s) {
   return (int)g;
 }
 
+template <bool KEEP, bool STATUS, bool PINHOLE>
+void launch_lin3(int grid, cudaStream_t st, const LinArgs& a, bool pdl) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kLinThreads);
+  cfg.dynamicSmemBytes = kLinSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, picp_linearize_kernel<KEEP, STATUS, PINHOLE>, a);
+}
+
 template <bool KEEP, bool STATUS>
-void launch_lin2(bool pinhole, int grid, cudaStream_t st, const LinArgs& a) {
-  if (pinhole) picp_linearize_kernel<KEEP, STATUS, true><<<grid, kLinThreads, kLinSmemBytes, st>>>(a);
-  else picp_linearize_kernel<KEEP, STATUS, false><<<grid, kLinThreads, kLinSmemBytes, st>>>(a);
+void launch_lin2(bool pinhole, int grid, cudaStream_t st, const LinArgs& a, bool pdl) {
+  if (pinhole) launch_lin3<KEEP, STATUS, true>(grid, st, a, pdl);
+  else launch_lin3<KEEP, STATUS, false>(grid, st, a, pdl);
 }
 
 int launch_linearize(vo_picp* s, float thr, float damping, bool keep, bool status, bool fuse_solve) {
@@ -614,12 +652,14 @@ int launch_linearize(vo_picp* s, float thr, float damping, bool keep, bool statu
   a.peer_rank = ctx->peer_rank;
   for (int p = 0; p < VO_MAX_PEERS; ++p) a.peers[p] = (VoMailbox*)ctx->peer_mailbox[p];
   const int grid = grid_for(s);
+  // programmatic dependent launch only between the fused single-launch rounds (no NCCL call in between)
+  const bool pdl = fuse_solve && !status;
   if (keep) {
-    if (status) launch_lin2<true, true>(s->pinhole, grid, ctx->stream, a);
-    else launch_lin2<true, false>(s->pinhole, grid, ctx->stream, a);
+    if (status) launch_lin2<true, true>(s->pinhole, grid, ctx->stream, a, pdl);
+    else launch_lin2<true, false>(s->pinhole, grid, ctx->stream, a, pdl);
   } else {
-    if (status) launch_lin2<false, true>(s->pinhole, grid, ctx->stream, a);
-    else launch_lin2<false, false>(s->pinhole, grid, ctx->stream, a);
+    if (status) launch_lin2<false, true>(s->pinhole, grid, ctx->stream, a, pdl);
+    else launch_lin2<false, false>(s->pinhole, grid, ctx->stream, a, pdl);
   }
   VO_CHECK_LAUNCH(ctx, "picp_linearize_kernel");
   return VO_OK;
