@@ -112,6 +112,18 @@ __device__ __forceinline__ f2 mul2(f2 a, f2 b) {
   return d;
 }
 __device__ __forceinline__ f2 neg2(f2 a) { return a ^ 0x8000000080000000ull; }
+__device__ __forceinline__ f2 add2(f2 a, f2 b) {
+  f2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f2 sub2(f2 a, f2 b) {
+  f2 d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// a*b rounded once and never contracted into a following add (see the note in picp_pair)
+__device__ __forceinline__ f2 prod2(f2 a, f2 b) { return fma2(a, b, 0ull); }
 
 // Two correspondences: exact part per point, then J, H += lambda J^T J and b += lambda J^T e in packed
 // f32x2 (lane 0 = first point, lane 1 = second; acc2[k] holds the two lanes' partial sums of slot k).
@@ -121,8 +133,66 @@ __device__ __forceinline__ void picp_pair(const PicpCam& cam, const float* __res
                                           float px0, float py0, float pz0, float zu0, float zv0,
                                           float px1, float py1, float pz1, float zu1, float zv1, bool v0, bool v1,
                                           f2 (&acc2)[29], int& n_in, int& n_out, int& st0, int& st1) {
-  PointTerms t0 = picp_project<PINHOLE>(cam, T, thr, px0, py0, pz0, zu0, zv0, v0);
-  PointTerms t1 = picp_project<PINHOLE>(cam, T, thr, px1, py1, pz1, zu1, zv1, v1);
+  // ---- exact part of BOTH points in packed f32x2 (camera.h:24-36, picp_solver.cpp:32-36,74).  Every
+  // product is rounded on its own (prod2 = fma with a +0 addend: ptxas would otherwise contract
+  // mul.rn.f32x2 + add.rn.f32x2 into FFMA2) and the additions follow Eigen's x0 + (x1 + x2) order, so each
+  // lane computes bit for bit what picp_project<> (vo_device.cuh) computes for one point.
+  PointTerms t0, t1;
+  {
+    const f2 px = pack2(px0, px1), py = pack2(py0, py1), pz = pack2(pz0, pz1);
+    auto bc = [](float x) { return pack2(x, x); };
+    const f2 c0 = add2(bc(T[3]), add2(prod2(bc(T[0]), px), add2(prod2(bc(T[1]), py), prod2(bc(T[2]), pz))));
+    const f2 c1 = add2(bc(T[7]), add2(prod2(bc(T[4]), px), add2(prod2(bc(T[5]), py), prod2(bc(T[6]), pz))));
+    const f2 c2 = add2(bc(T[11]), add2(prod2(bc(T[8]), px), add2(prod2(bc(T[9]), py), prod2(bc(T[10]), pz))));
+    unpack2(c0, t0.c0, t1.c0);
+    unpack2(c1, t0.c1, t1.c1);
+    unpack2(c2, t0.c2, t1.c2);
+    f2 q0 = 0ull, q1 = 0ull, iz = 0ull;
+    if (PINHOLE) {  // shortcut values for both lanes (see picp_project<> for why they are exact)
+      q0 = add2(prod2(bc(cam.K[0]), c0), prod2(bc(cam.K[2]), c2));
+      q1 = add2(prod2(bc(cam.K[4]), c1), prod2(bc(cam.K[5]), c2));
+      float r0, r1;
+      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(t0.c2));
+      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(t1.c2));
+      const f2 r = pack2(r0, r1);
+      iz = fma2(r, fma2(c2, pack2(-r0, -r1), bc(1.f)), r);
+    }
+    unpack2(q0, t0.q0, t1.q0);
+    unpack2(q1, t0.q1, t1.q1);
+    unpack2(iz, t0.iz, t1.iz);
+    const bool sc0 = PINHOLE && (t0.c2 >= 1e-30f) && (t0.c2 <= 1e30f) && finite_f(t0.c0) && finite_f(t0.c1);
+    const bool sc1 = PINHOLE && (t1.c2 >= 1e-30f) && (t1.c2 <= 1e30f) && finite_f(t1.c0) && finite_f(t1.c1);
+    if ((!sc0 && !(t0.c2 <= 0.f)) || (!sc1 && !(t1.c2 <= 0.f))) {
+      // rare: the reference's arithmetic verbatim (general K, IEEE reciprocal) for the lane that needs it
+      if (!sc0 && !(t0.c2 <= 0.f)) {
+        t0.q0 = dot3_rn(cam.K[0], t0.c0, cam.K[1], t0.c1, cam.K[2], t0.c2);
+        t0.q1 = dot3_rn(cam.K[3], t0.c0, cam.K[4], t0.c1, cam.K[5], t0.c2);
+        t0.iz = __frcp_rn(dot3_rn(cam.K[6], t0.c0, cam.K[7], t0.c1, cam.K[8], t0.c2));
+      }
+      if (!sc1 && !(t1.c2 <= 0.f)) {
+        t1.q0 = dot3_rn(cam.K[0], t1.c0, cam.K[1], t1.c1, cam.K[2], t1.c2);
+        t1.q1 = dot3_rn(cam.K[3], t1.c0, cam.K[4], t1.c1, cam.K[5], t1.c2);
+        t1.iz = __frcp_rn(dot3_rn(cam.K[6], t1.c0, cam.K[7], t1.c1, cam.K[8], t1.c2));
+      }
+      q0 = pack2(t0.q0, t1.q0);
+      q1 = pack2(t0.q1, t1.q1);
+      iz = pack2(t0.iz, t1.iz);
+    }
+    const f2 u = prod2(q0, iz), v = prod2(q1, iz);
+    float u0, u1, w0, w1;
+    unpack2(u, u0, u1);
+    unpack2(v, w0, w1);
+    // camera.h:27,31-34 with their NaN behaviour: a NaN compares false and stays "inside"
+    const bool ins0 = v0 && !(t0.c2 <= 0.f) && !(u0 < 0.f) && !(u0 > cam.umax) && !(w0 < 0.f) && !(w0 > cam.vmax);
+    const bool ins1 = v1 && !(t1.c2 <= 0.f) && !(u1 < 0.f) && !(u1 > cam.umax) && !(w1 < 0.f) && !(w1 > cam.vmax);
+    const f2 e0 = sub2(u, pack2(zu0, zu1)), e1 = sub2(v, pack2(zv0, zv1));
+    const f2 chi = add2(prod2(e0, e0), prod2(e1, e1));
+    unpack2(e0, t0.e0, t1.e0);
+    unpack2(e1, t0.e1, t1.e1);
+    unpack2(chi, t0.chi, t1.chi);
+    t0.st = ins0 ? ((t0.chi > thr) ? VO_PICP_OUTLIER : VO_PICP_INLIER) : VO_PICP_SKIPPED;
+    t1.st = ins1 ? ((t1.chi > thr) ? VO_PICP_OUTLIER : VO_PICP_INLIER) : VO_PICP_SKIPPED;
+  }
   st0 = t0.st;
   st1 = t1.st;
   const bool in0 = t0.st == VO_PICP_INLIER, in1 = t1.st == VO_PICP_INLIER;
