@@ -9,9 +9,9 @@
 //   pairs      int32[2*C]   AoS exactly as IntPairVector (first: image, second: world)
 //   packed     float[5][Cp] SoA stream gathered ONCE per correspondence set by
 //              picp_pack_kernel: wx, wy, wz, zu, zv; Cp = C rounded up to 4.  Every
-//              Gauss-Newton round then streams 20 B/correspondence: tiles of 1536
-//              correspondences (5 x 6 KB) are staged into a 4-deep shared-memory ring by one
-//              producer lane with cp.async.bulk (TMA) + mbarrier, and 12 consumer warps read
+//              Gauss-Newton round then streams 20 B/correspondence: tiles of 1408
+//              correspondences (5 x 5.5 KB) are staged into a 4-deep shared-memory ring by one
+//              producer lane with cp.async.bulk (TMA) + mbarrier, and 11 consumer warps read
 //              them back as float4, each thread owning 4 consecutive correspondences per tile
 //              (two pairs; each pair runs through packed f32x2 arithmetic).
 //   partials   float[grid][32]  per-block sums, fixed slot order
@@ -38,7 +38,7 @@
 namespace {
 
 #ifndef VO_LIN_THREADS
-#define VO_LIN_THREADS 384
+#define VO_LIN_THREADS 352
 #endif
 #ifndef VO_LIN_CTAS
 #define VO_LIN_CTAS 1
@@ -46,8 +46,9 @@ namespace {
 #ifndef VO_LIN_STAGES
 #define VO_LIN_STAGES 4
 #endif
-// 384 consumer threads + 1 producer warp, one CTA per SM: the packed even/odd accumulators need ~128
-// registers per thread; measured on B200 (exp/ab.sh): 256x2 spills (110 us), 384x1 67 us, 448x1 74 us.
+// 352 consumer threads + 1 producer warp = 12 warps, one CTA per SM: the packed even/odd accumulators want
+// ~150 registers per thread. Measured on B200 (exp/ab.sh, us per 10M-correspondence round): 256x2 CTAs spills,
+// 256: 58.2, 320: 57.3, 352: 53.7, 384: 55.7, 448: 59.5, 480: 56.3.
 constexpr int kThreads = VO_LIN_THREADS;  // consumer threads per CTA of the linearize kernel
 constexpr int kWarps = kThreads / 32;
 constexpr int kSlots = 32;       // partial row: 0..20 H, 21..26 b, 27 chi_in, 28 chi_out, 29 n_in, 30 n_out
@@ -383,7 +384,11 @@ constexpr int kLinThreads = kThreads + 32;  // 8 consumer warps + 1 producer war
 constexpr size_t kLinSmemBytes = (size_t)kStages * 5 * kTile * sizeof(float);
 
 template <bool KEEP, bool STATUS, bool PINHOLE>
+#ifdef VO_LIN_MAXNREG
+__global__ void __maxnreg__(VO_LIN_MAXNREG) picp_linearize_kernel(const LinArgs a) {
+#else
 __global__ void __launch_bounds__(kLinThreads, kCtasPerSm) picp_linearize_kernel(const LinArgs a) {
+#endif
   // Programmatic dependent launch: the next round's grid may start launching right away; its CTAs run this
   // prologue (barrier init, first TMA tiles: the packed planes do not change between rounds) on the SMs this
   // grid has already left, i.e. under the solve tail, and block in griddepcontrol.wait until this grid has
