@@ -353,19 +353,21 @@ __device__ __forceinline__ double picp_peer_allreduce(const LinArgs& a, double m
   __threadfence_system();
   __syncwarp();
   if (lane < a.peer_n) *(volatile unsigned*)&a.peers[lane]->flags[par][a.peer_rank] = seq;
-  double total = 0.0;
+  // lane q waits for rank q's flag (all peers in parallel), then ONE system-scope fence orders the slot reads
   bool ok = true;
-  for (int q = 0; q < a.peer_n; ++q) {
+  if (lane < a.peer_n) {
     long long spins = 0;
-    while (*(volatile unsigned*)&me->flags[par][q] != seq) {
+    while (*(volatile unsigned*)&me->flags[par][lane] != seq) {
       if (++spins > (1ll << 24)) {  // ~5 s: a peer never launched its round; flag it instead of hanging the GPU
         ok = false;
         break;
       }
     }
-    __threadfence_system();
-    total += *(volatile double*)&me->slots[par][q][lane];
   }
+  ok = __all_sync(0xffffffffu, ok);
+  __threadfence_system();
+  double total = 0.0;
+  for (int q = 0; q < a.peer_n; ++q) total += *(volatile double*)&me->slots[par][q][lane];
   __syncwarp();
   if (lane == 0) {
     *(volatile unsigned*)&me->seq = seq;

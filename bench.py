@@ -124,7 +124,7 @@ def run_reference(args):
                                        f"{threads} threads (oracle/vo_oracle.cpp, -O2, correspondence-parallel)"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
 
 
 def workload_config(n, exchange="fused peer stores over NVLink inside the linearize kernel"):
@@ -308,7 +308,7 @@ def run_cuda(args):
         if cpu_baseline:
             line["cpu_baseline"] = cpu_baseline
         line.update(extra)
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     solver.close()
     solver2.close()
     if multi:
@@ -480,6 +480,12 @@ def bench_small_frame(args, ctx, torch, dev, stream):
 
 
 def main():
+    # rank 0 prints ONE JSON line: native libraries (NCCL's version banner) write to fd 1 too, so fd 1 is
+    # pointed at stderr for the whole run and the JSON goes to the saved real stdout at the end
+    real_stdout = os.fdopen(os.dup(1), "w")
+    sys.stdout.flush()
+    os.dup2(2, 1)
+    sys.stdout = real_stdout
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
