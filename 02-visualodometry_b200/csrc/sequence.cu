@@ -86,7 +86,7 @@ __device__ __forceinline__ bool accept_match(int idx, float best, float second, 
   return (idx != -1) && (best < dist_thr) && (__fdiv_rn(best, second) < ratio_thr);
 }
 
-__global__ void __launch_bounds__(kSeqThreads) seq_pipeline_kernel(const SeqArgs a) {
+__global__ void __launch_bounds__(kSeqThreads, 4) seq_pipeline_kernel(const SeqArgs a) {
   __shared__ FrameBuf s_curr, s_next;
   __shared__ __align__(16) float s_tile[kSeqThreads * kDimPad];  // map descriptors, 128 rows at a time
   __shared__ int2 s_iw[kSeqThreads];                              // (image idx in next, world idx)
@@ -344,6 +344,9 @@ __global__ void __launch_bounds__(kSeqThreads) seq_pipeline_kernel(const SeqArgs
     // (3) estimated camera-in-world pose of the next frame
     if (tid == 0) {
       pose_inverse_dev(s_pose, s_est);
+      bool fin = true;
+      for (int i = 0; i < 12; ++i) fin = fin && finite_f(s_est[i]);
+      s_flag = fin ? 0 : 1;
       if (a.rounds) a.rounds[seq * a.n_frames + f + 1] = rounds_done;
       if (a.inliers) {
         a.inliers[(seq * a.n_frames + f + 1) * 2] = last_inl;
@@ -351,6 +354,13 @@ __global__ void __launch_bounds__(kSeqThreads) seq_pipeline_kernel(const SeqArgs
       }
     }
     __syncthreads();
+    if (s_flag) {  // tracking lost (non-finite pose): the reference would carry NaNs on; flag it and stop here
+      if (tid == 0) {
+        a.status[seq] = 3;
+        a.w_cnt[seq] = s_wcnt;
+      }
+      return;
+    }
     if (tid < 12) poses[(f + 1) * 12 + tid] = s_est[tid];
     // (4) current frame against the next frame
     best = FLT_MAX; second = FLT_MAX; idx = -1;

@@ -193,7 +193,8 @@ int vo_anti_join(vo_ctx* ctx, const int32_t* matched_id, int64_t n_matched,
  *   cnt[S][F]  uv[S][F][P][2]  desc[S][F][P][10]  id_real[S][F][P]      (id_meas = index inside the frame)
  *   poses[S][F][12] camera-in-world (frame 0 = identity)   world_xyz[S][W][3]  world_id[S][W]  world_cnt[S]
  *   rounds[S][F] (nullable)  inliers[S][F][2] = (inliers of the last round, correspondences) (nullable)
- *   status[S]: 0 ok, 1 map capacity reached (overflow dropped), 2 fewer than 8 initial matches (nothing done) */
+ *   status[S]: 0 ok, 1 map capacity reached (overflow dropped), 2 fewer than 8 initial matches (nothing done),
+ *              3 tracking lost (a non-finite pose came out of PICP; frames from there on keep the identity) */
 typedef struct vo_seq_params {
   float K[9];
   int32_t rows, cols;
