@@ -87,6 +87,41 @@ def run_icp_test(ds, backend, n_meas=121, log=None):
                 n_init_matches=len(m01), init_mask=mask)
 
 
+def run_vo(ds, backend, n_meas=120):
+    """The reference's older driver (exec/vo.cpp:55-214): Cam::initOneRound / Cam::oneRound = kernel threshold 1000,
+    exactly five rounds (src/cam.cpp:178-224), in the driver's own pose convention (getPose() = world-in-camera is
+    stored and handed to triangulatePoints as is)."""
+    poses = [I34.copy()]
+    world = World()
+    n_inl = []
+    for i in range(n_meas - 1):
+        p1, p2 = frame(ds, i), frame(ds, i + 1)
+        if i == 0:
+            m, _ = backend.match(p1["desc"], p2["desc"], p1["id_real"], p2["id_real"])
+            R, t, _ = backend.essential_recover(K_REF, p1["uv"][m[:, 0]], p2["uv"][m[:, 1]])
+            T = np.concatenate([R.astype(np.float32), t.astype(np.float32).reshape(3, 1)], 1)
+            est = backend.pose_inverse(T)
+            world.append(backend.triangulate(K_REF, I34, est, p1["uv"][m[:, 0]], p2["uv"][m[:, 1]]), p1, m[:, 0])
+            poses.append(est)
+            continue
+        iw, _ = backend.match(p2["desc"], world.desc, p2["id_real"], world.id_real)
+        prev = poses[-1]
+        solver = backend.picp_init(K_REF, ROWS, COLS, prev, world.xyz, p2["uv"], iw)
+        inl = 0
+        for _ in range(5):
+            _, _, inl = backend.picp_one_round(solver, 1000.0, 1.0, False)
+        est = backend.picp_pose(solver)
+        backend.picp_free(solver)
+        poses.append(est)
+        n_inl.append((inl, len(iw)))
+        im, _ = backend.match(p1["desc"], p2["desc"], p1["id_real"], p2["id_real"])
+        keep = backend.anti_join(p2["id_meas"][iw[:, 0]], p2["id_meas"][im[:, 1]])
+        new = im[keep]
+        if len(new):
+            world.append(backend.triangulate(K_REF, prev, est, p1["uv"][new[:, 0]], p2["uv"][new[:, 1]]), p1, new[:, 0])
+    return dict(poses=np.stack(poses), world=world, inliers=np.array(n_inl))
+
+
 def augment_pose(p):  # src/my_utilities.cpp:245-260
     T = np.eye(4, dtype=np.float64)[:3]
     c, s = np.cos(np.float32(p[2])), np.sin(np.float32(p[2]))

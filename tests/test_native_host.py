@@ -15,8 +15,33 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BIN = os.path.join(ROOT, "02-visualodometry_b200", "host", "icp_test_native")
 
 
+VO_BIN = os.path.join(ROOT, "02-visualodometry_b200", "host", "vo_native")
+
+
 def test_native_binary_is_built():
     assert os.path.exists(BIN), "build first: python -c 'import __graft_entry__ as g; g.build()'"
+    assert os.path.exists(VO_BIN)
+
+
+@pytest.mark.gpu
+def test_native_vo_driver(dataset, tmp_path):
+    """exec/vo.cpp's flow (Cam::initOneRound/oneRound: threshold 1000, five rounds): the C++ mirror, the Python
+    replay through the C-ABI and the oracle replay agree; free oneRound()'s parameters (threshold 100, outliers
+    kept) are covered by tests/test_gpu_picp.py."""
+    prefix = dataset_io.write_meas_files(dataset, str(tmp_path / "data"), n_meas=120)
+    out = tmp_path / "vo_poses.txt"
+    r = subprocess.run([VO_BIN, prefix, str(out), "120"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    native = np.loadtxt(out).reshape(-1, 3, 4)
+    assert native.shape[0] == 120
+    gpu = replay.run_vo(dataset, backends.GpuBackend())
+    cpu = replay.run_vo(dataset, backends.OracleBackend())
+    assert np.abs(native - gpu["poses"]).max() <= 1e-5          # same calls, printed with 9 digits
+    assert len(gpu["world"].xyz) == len(cpu["world"].xyz)
+    assert np.array_equal(gpu["world"].id_real, cpu["world"].id_real)
+    assert np.array_equal(gpu["inliers"][:, 1], cpu["inliers"][:, 1])
+    assert np.abs(gpu["poses"] - cpu["poses"]).max() <= 5e-3
+    assert "Number of duplicate world points" in r.stdout
 
 
 def test_native_refuses_to_run_without_gpu(dataset, tmp_path):
