@@ -162,16 +162,14 @@ __global__ void __launch_bounds__(kMatchThreads) match_scan10_kernel(
       sB[(jj >> 1) * kPairFloats + dim_slot10(k) * 2 + (jj & 1)] = __ldg(B + (j0 + src) * DIM + k);
     }
     __syncthreads();
-#pragma unroll 2
-    for (int p = 0; p < n_pairs; ++p) {
-      const float4* rec = reinterpret_cast<const float4*>(sB + p * kPairFloats);
+    // two column pairs per step: their lower bounds are independent, which hides the LDS and FP latencies
+    auto lower_bound = [&](const float4* rec) {
       const float4 v0 = rec[0], v1 = rec[1];  // dims (0,4) and (2,6) of both columns
       const f2 x0 = sq2(pack2(v0.x, v0.y), a[0]), x4 = sq2(pack2(v0.z, v0.w), a[1]);
       const f2 x2 = sq2(pack2(v1.x, v1.y), a[2]), x6 = sq2(pack2(v1.z, v1.w), a[3]);
-      const f2 lb = add2(add2(x0, x4), add2(x2, x6));  // p0[0] + p0[2]
-      float lb0, lb1;
-      unpack2(lb, lb0, lb1);
-      if (!__any_sync(0xffffffffu, (lb0 < second) || (lb1 < second))) continue;
+      return add2(add2(x0, x4), add2(x2, x6));  // p0[0] + p0[2]
+    };
+    auto finish = [&](const float4* rec, f2 lb, int p) {
       const float4 v2 = rec[2], v3 = rec[3], v4 = rec[4];
       const f2 x1 = sq2(pack2(v2.x, v2.y), a[4]), x5 = sq2(pack2(v2.z, v2.w), a[5]);
       const f2 x3 = sq2(pack2(v3.x, v3.y), a[6]), x7 = sq2(pack2(v3.z, v3.w), a[7]);
@@ -183,6 +181,24 @@ __global__ void __launch_bounds__(kMatchThreads) match_scan10_kernel(
       const int j = (int)(j0 + 2 * p);
       update_best(d0, j, best, second, idx);
       if (2 * p + 1 < cnt) update_best(d1, j + 1, best, second, idx);
+    };
+    auto may_improve = [&](f2 lb) {
+      float lb0, lb1;
+      unpack2(lb, lb0, lb1);
+      return __any_sync(0xffffffffu, (lb0 < second) || (lb1 < second));
+    };
+    int p = 0;
+    for (; p + 2 <= n_pairs; p += 2) {
+      const float4* recA = reinterpret_cast<const float4*>(sB + p * kPairFloats);
+      const float4* recB = reinterpret_cast<const float4*>(sB + (p + 1) * kPairFloats);
+      const f2 lbA = lower_bound(recA), lbB = lower_bound(recB);
+      if (may_improve(lbA)) finish(recA, lbA, p);      // ascending column order keeps the lowest-index tie-break
+      if (may_improve(lbB)) finish(recB, lbB, p + 1);
+    }
+    if (p < n_pairs) {
+      const float4* rec = reinterpret_cast<const float4*>(sB + p * kPairFloats);
+      const f2 lb = lower_bound(rec);
+      if (may_improve(lb)) finish(rec, lb, p);
     }
   }
   if (valid) {
@@ -254,6 +270,203 @@ __global__ void match_keys10_kernel(const float* __restrict__ A, long long row_b
   }
   keys[r] = key;
   ids[r] = (unsigned)r;
+}
+
+// ---- spatial index over the columns (D = 10, large problems): columns sorted along the same Morton curve as
+// the query rows, stored as pair records (the shared-memory tile layout, so a tile load is a straight float4
+// copy), plus the bounding box of every 256-column tile in the four lower-bound dimensions.
+__global__ void match_gather10_kernel(const float* __restrict__ B, const unsigned* __restrict__ order, long long n2,
+                                      float* __restrict__ rec, int* __restrict__ orig) {
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // sorted position
+  const long long n2p = (n2 + 1) & ~1ll;
+  if (j >= n2p) return;
+  const long long src = order[j < n2 ? j : n2 - 1];  // an odd tail is padded with a copy of the last column
+  orig[j] = (int)src;
+#pragma unroll
+  for (int k = 0; k < 10; ++k) rec[(j >> 1) * kPairFloats + dim_slot10(k) * 2 + (j & 1)] = __ldg(B + src * 10 + k);
+}
+
+__global__ void __launch_bounds__(kTileRows) match_tilebox10_kernel(const float* __restrict__ rec, long long n2,
+                                                                    float* __restrict__ box /* [tiles][8] */) {
+  __shared__ float s_lo[kTileRows / 32][4], s_hi[kTileRows / 32][4];
+  const long long j = (long long)blockIdx.x * kTileRows + threadIdx.x;
+  float lo[4], hi[4];
+#pragma unroll
+  for (int d = 0; d < 4; ++d) {
+    const float v = (j < n2) ? rec[(j >> 1) * kPairFloats + d * 2 + (j & 1)] : NAN;  // slots 0..3 = dims 0,4,2,6
+    lo[d] = hi[d] = v;  // fminf / fmaxf ignore NaN
+  }
+#pragma unroll
+  for (int d = 0; d < 4; ++d)
+    for (int o = 16; o > 0; o >>= 1) {
+      lo[d] = fminf(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], o));
+      hi[d] = fmaxf(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], o));
+    }
+  if ((threadIdx.x & 31) == 0)
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+      s_lo[threadIdx.x >> 5][d] = lo[d];
+      s_hi[threadIdx.x >> 5][d] = hi[d];
+    }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    float l = s_lo[0][threadIdx.x], h = s_hi[0][threadIdx.x];
+    for (int w = 1; w < kTileRows / 32; ++w) {
+      l = fminf(l, s_lo[w][threadIdx.x]);
+      h = fmaxf(h, s_hi[w][threadIdx.x]);
+    }
+    box[(size_t)blockIdx.x * 8 + threadIdx.x] = l;
+    box[(size_t)blockIdx.x * 8 + 4 + threadIdx.x] = h;
+  }
+}
+
+// my_utilities.h:93-99 when the columns are NOT visited in index order: equal distances must still resolve to the
+// lowest index, and `second` is the second smallest value of the multiset (both are order independent).
+__device__ __forceinline__ void update_best_tie(float d, int j, float& best, float& second, int& idx) {
+  const bool lt = (d < best) || (d == best && j < idx);
+  const float s2 = (d < second) ? d : second;
+  second = lt ? best : s2;
+  idx = lt ? j : idx;
+  best = lt ? d : best;
+}
+
+// Scan with tile skipping. A CTA owns 128 Morton-adjacent query rows; it walks the column tiles outward from its
+// own position on the curve and skips a tile when the squared distance between its rows' box and the tile's box
+// (in the lower-bound dimensions) cannot be below any row's current second-best.
+//   exactness: lb_float(row, col) >= lb_real * (1 - 4 ulp) >= box_real * (1 - 4 ulp) > box_float * (1 - 1e-5),
+//   so box_float * (1 - 1e-5) >= second  =>  lb_float >= second  =>  the column cannot change the row's result.
+__global__ void __launch_bounds__(kMatchThreads) match_scan10_indexed_kernel(
+    const float* __restrict__ A, long long row_begin, long long rows, const unsigned* __restrict__ row_order,
+    const unsigned* __restrict__ row_keys_sorted, const float* __restrict__ rec, const int* __restrict__ orig,
+    const float* __restrict__ box, const unsigned* __restrict__ col_keys_sorted, long long n2,
+    float* __restrict__ o_best, float* __restrict__ o_second, int* __restrict__ o_idx) {
+  constexpr int DIM = 10;
+  __shared__ __align__(16) float sB[(kTileRows / 2) * kPairFloats];
+  __shared__ int sOrig[kTileRows];
+  __shared__ float s_lo[kMatchThreads / 32][4], s_hi[kMatchThreads / 32][4];
+  __shared__ int s_max[kMatchThreads / 32];
+  __shared__ long long s_t0;
+  const long long slot = (long long)blockIdx.x * kMatchThreads + threadIdx.x;
+  const bool valid = slot < rows;
+  const long long r = valid ? (long long)row_order[slot] : 0;
+  f2 a[DIM];
+  float lo[4], hi[4];
+#pragma unroll
+  for (int k = 0; k < DIM; ++k) {
+    const float v = valid ? __ldg(A + (row_begin + r) * DIM + k) : NAN;
+    a[dim_slot10(k)] = pack2(v, v);
+  }
+#pragma unroll
+  for (int d = 0; d < 4; ++d) {
+    float v, w;
+    unpack2(a[d], v, w);
+    lo[d] = hi[d] = v;
+    for (int o = 16; o > 0; o >>= 1) {
+      lo[d] = fminf(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], o));
+      hi[d] = fmaxf(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+      s_lo[threadIdx.x >> 5][d] = lo[d];
+      s_hi[threadIdx.x >> 5][d] = hi[d];
+    }
+  }
+  if (threadIdx.x == 0) {  // where this CTA's rows sit among the sorted columns
+    const long long mid = min(slot + kMatchThreads / 2, rows - 1);
+    const unsigned key = row_keys_sorted[mid];
+    long long a0 = 0, a1 = n2;
+    while (a0 < a1) {
+      const long long m = (a0 + a1) >> 1;
+      if (col_keys_sorted[m] < key) a0 = m + 1;
+      else a1 = m;
+    }
+    s_t0 = min(a0, n2 - 1) / kTileRows;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int d = 0; d < 4; ++d) {
+    lo[d] = s_lo[0][d];
+    hi[d] = s_hi[0][d];
+    for (int w = 1; w < kMatchThreads / 32; ++w) {
+      lo[d] = fminf(lo[d], s_lo[w][d]);
+      hi[d] = fmaxf(hi[d], s_hi[w][d]);
+    }
+  }
+  float best = FLT_MAX, second = FLT_MAX, cta_second = FLT_MAX;
+  int idx = -1;
+  const long long n_tiles = (n2 + kTileRows - 1) / kTileRows;
+  long long up = s_t0, down = s_t0 - 1;
+  for (long long step = 0; step < n_tiles; ++step) {
+    long long t;
+    if ((step & 1) == 0) t = (up < n_tiles) ? up++ : down--;
+    else t = (down >= 0) ? down-- : up++;
+    // box-to-box lower bound of every (row, column) partial distance of this tile
+    const float4 bl = __ldg(reinterpret_cast<const float4*>(box) + 2 * t), bh = __ldg(reinterpret_cast<const float4*>(box) + 2 * t + 1);
+    const float g0 = fmaxf(0.f, fmaxf(bl.x - hi[0], lo[0] - bh.x)), g1 = fmaxf(0.f, fmaxf(bl.y - hi[1], lo[1] - bh.y));
+    const float g2 = fmaxf(0.f, fmaxf(bl.z - hi[2], lo[2] - bh.z)), g3 = fmaxf(0.f, fmaxf(bl.w - hi[3], lo[3] - bh.w));
+    const float bound = (g0 * g0 + g1 * g1 + g2 * g2 + g3 * g3) * 0.99999f;
+    if (bound >= cta_second) continue;  // uniform over the CTA; NaN bounds never skip
+    const long long j0 = t * kTileRows;
+    const int cnt = (int)((n2 - j0 < kTileRows) ? (n2 - j0) : kTileRows);
+    const int n_pairs = (cnt + 1) >> 1;
+    __syncthreads();
+    {
+      const float4* src = reinterpret_cast<const float4*>(rec + (j0 >> 1) * kPairFloats);
+      float4* dst = reinterpret_cast<float4*>(sB);
+      for (int q = threadIdx.x; q < n_pairs * (kPairFloats / 4); q += kMatchThreads) dst[q] = __ldg(src + q);
+      for (int q = threadIdx.x; q < 2 * n_pairs; q += kMatchThreads) sOrig[q] = __ldg(orig + j0 + q);
+    }
+    __syncthreads();
+    auto lower_bound = [&](const float4* rc) {
+      const float4 v0 = rc[0], v1 = rc[1];
+      const f2 x0 = sq2(pack2(v0.x, v0.y), a[0]), x4 = sq2(pack2(v0.z, v0.w), a[1]);
+      const f2 x2 = sq2(pack2(v1.x, v1.y), a[2]), x6 = sq2(pack2(v1.z, v1.w), a[3]);
+      return add2(add2(x0, x4), add2(x2, x6));
+    };
+    auto finish = [&](const float4* rc, f2 lb, int p) {
+      const float4 v2 = rc[2], v3 = rc[3], v4 = rc[4];
+      const f2 x1 = sq2(pack2(v2.x, v2.y), a[4]), x5 = sq2(pack2(v2.z, v2.w), a[5]);
+      const f2 x3 = sq2(pack2(v3.x, v3.y), a[6]), x7 = sq2(pack2(v3.z, v3.w), a[7]);
+      const f2 x8 = sq2(pack2(v4.x, v4.y), a[8]), x9 = sq2(pack2(v4.z, v4.w), a[9]);
+      f2 d = add2(lb, add2(add2(x1, x5), add2(x3, x7)));
+      d = add2(add2(d, x8), x9);
+      float d0, d1;
+      unpack2(d, d0, d1);
+      update_best_tie(d0, sOrig[2 * p], best, second, idx);
+      if (2 * p + 1 < cnt) update_best_tie(d1, sOrig[2 * p + 1], best, second, idx);
+    };
+    auto may_improve = [&](f2 lb) {
+      float lb0, lb1;
+      unpack2(lb, lb0, lb1);
+      return __any_sync(0xffffffffu, (lb0 < second) || (lb1 < second));
+    };
+    int p = 0;
+    for (; p + 2 <= n_pairs; p += 2) {
+      const float4* recA = reinterpret_cast<const float4*>(sB + p * kPairFloats);
+      const float4* recB = reinterpret_cast<const float4*>(sB + (p + 1) * kPairFloats);
+      const f2 lbA = lower_bound(recA), lbB = lower_bound(recB);
+      if (may_improve(lbA)) finish(recA, lbA, p);
+      if (may_improve(lbB)) finish(recB, lbB, p + 1);
+    }
+    if (p < n_pairs) {
+      const float4* rc = reinterpret_cast<const float4*>(sB + p * kPairFloats);
+      const f2 lb = lower_bound(rc);
+      if (may_improve(lb)) finish(rc, lb, p);
+    }
+    // the loosest second-best of the CTA decides what can still be skipped (second >= 0: int order = float order)
+    const int mine = valid ? __float_as_int(second) : 0;
+    const int wmax = __reduce_max_sync(0xffffffffu, mine);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = wmax;
+    __syncthreads();
+    int m = s_max[0];
+    for (int w = 1; w < kMatchThreads / 32; ++w) m = max(m, s_max[w]);
+    cta_second = __int_as_float(m);
+  }
+  if (valid) {
+    o_best[r] = best;
+    o_second[r] = second;
+    o_idx[r] = idx;
+  }
 }
 
 // merge the per-split triples in ascending split order (exact: comparisons only), apply the
@@ -485,15 +698,30 @@ int vo_match_dev(vo_ctx* ctx, const float* d_descA, int64_t n1, const float* d_d
   const size_t o_pi = carve((size_t)n_splits * rows * 4), o_idx = carve((size_t)rows * 4);
   const size_t o_flags = carve((size_t)rows), o_counts = carve((size_t)merge_blocks * 4);
   const size_t o_small = carve(64), o_table = carve((size_t)table_size * 8);
-  // optional Morton ordering of the query rows (D = 10 pruned scan)
+  // optional Morton ordering of the query rows (D = 10 pruned scan) and, for large column sets, of the columns
+  // too (tile boxes + tile skipping)
   const bool ordered = (dim == 10) && rows >= kSortMinRows && n2 > 0;
+  const bool indexed = ordered && n2 >= kSortMinRows;
+  if (indexed) n_splits = 1;
   size_t sort_tmp_bytes = 0;
-  if (ordered)
+  if (ordered) {
     cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp_bytes, (const unsigned*)nullptr, (unsigned*)nullptr,
                                     (const unsigned*)nullptr, (unsigned*)nullptr, (int)rows, 0, 32, ctx->stream);
+    if (indexed) {
+      size_t b2 = 0;
+      cub::DeviceRadixSort::SortPairs(nullptr, b2, (const unsigned*)nullptr, (unsigned*)nullptr, (const unsigned*)nullptr,
+                                      (unsigned*)nullptr, (int)n2, 0, 32, ctx->stream);
+      if (b2 > sort_tmp_bytes) sort_tmp_bytes = b2;
+    }
+  }
+  const long long n2p = (n2 + 1) & ~1ll, n_tiles = (n2 + kTileRows - 1) / kTileRows;
   const size_t o_keys = carve(ordered ? (size_t)rows * 4 : 0), o_keys2 = carve(ordered ? (size_t)rows * 4 : 0);
   const size_t o_ids = carve(ordered ? (size_t)rows * 4 : 0), o_order = carve(ordered ? (size_t)rows * 4 : 0);
   const size_t o_mm = carve(64), o_sorttmp = carve(sort_tmp_bytes);
+  const size_t o_ckeys = carve(indexed ? (size_t)n2 * 4 : 0), o_ckeys2 = carve(indexed ? (size_t)n2 * 4 : 0);
+  const size_t o_cids = carve(indexed ? (size_t)n2 * 4 : 0), o_corder = carve(indexed ? (size_t)n2 * 4 : 0);
+  const size_t o_rec = carve(indexed ? (size_t)n2p * 10 * 4 : 0), o_orig = carve(indexed ? (size_t)n2p * 4 : 0);
+  const size_t o_box = carve(indexed ? (size_t)n_tiles * 32 : 0);
   char* base;
   st = vo_scratch(ctx, off, (void**)&base);
   if (st) return st;
@@ -520,17 +748,44 @@ int vo_match_dev(vo_ctx* ctx, const float* d_descA, int64_t n1, const float* d_d
     VO_CUDA(ctx, cudaMemsetAsync(mm + 4, 0x00, 16, ctx->stream));
     match_minmax10_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(d_descA, row_begin, rows, mm);
     VO_CHECK_LAUNCH(ctx, "match_minmax10_kernel");
+    if (indexed) {  // one key range for rows and columns
+      match_minmax10_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(d_descB, 0, n2, mm);
+      VO_CHECK_LAUNCH(ctx, "match_minmax10_kernel");
+    }
     match_keys10_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, ctx->stream>>>(d_descA, row_begin, rows, mm, keys, ids);
     VO_CHECK_LAUNCH(ctx, "match_keys10_kernel");
     VO_CUDA(ctx, cub::DeviceRadixSort::SortPairs(base + o_sorttmp, sort_tmp_bytes, keys, keys2, ids, sorted_ids,
                                                  (int)rows, 0, 32, ctx->stream));
     ctx->launches += 4;  // CUB's histogram + onesweep passes
     order = sorted_ids;
+    if (indexed) {
+      unsigned* ckeys = (unsigned*)(base + o_ckeys);
+      unsigned* ckeys2 = (unsigned*)(base + o_ckeys2);
+      unsigned* cids = (unsigned*)(base + o_cids);
+      unsigned* corder = (unsigned*)(base + o_corder);
+      float* rec = (float*)(base + o_rec);
+      int* orig = (int*)(base + o_orig);
+      float* box = (float*)(base + o_box);
+      match_keys10_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, ctx->stream>>>(d_descB, 0, n2, mm, ckeys, cids);
+      VO_CHECK_LAUNCH(ctx, "match_keys10_kernel");
+      VO_CUDA(ctx, cub::DeviceRadixSort::SortPairs(base + o_sorttmp, sort_tmp_bytes, ckeys, ckeys2, cids, corder, (int)n2, 0,
+                                                   32, ctx->stream));
+      ctx->launches += 4;
+      match_gather10_kernel<<<(unsigned)((n2p + 255) / 256), 256, 0, ctx->stream>>>(d_descB, corder, n2, rec, orig);
+      VO_CHECK_LAUNCH(ctx, "match_gather10_kernel");
+      match_tilebox10_kernel<<<(unsigned)n_tiles, kTileRows, 0, ctx->stream>>>(rec, n2, box);
+      VO_CHECK_LAUNCH(ctx, "match_tilebox10_kernel");
+      match_scan10_indexed_kernel<<<(unsigned)row_blocks, kMatchThreads, 0, ctx->stream>>>(
+          d_descA, row_begin, rows, sorted_ids, keys2, rec, orig, box, ckeys2, n2, pb, ps, pi);
+      VO_CHECK_LAUNCH(ctx, "match_scan10_indexed_kernel");
+    }
   }
-  scan_fn scan = scan_for_dim(dim);
-  dim3 grid((unsigned)row_blocks, (unsigned)n_splits);
-  scan(grid, ctx->stream, d_descA, row_begin, row_end, d_descB, n2, split_size, order, pb, ps, pi);
-  VO_CHECK_LAUNCH(ctx, "match_scan_kernel");
+  if (!indexed) {
+    scan_fn scan = scan_for_dim(dim);
+    dim3 grid((unsigned)row_blocks, (unsigned)n_splits);
+    scan(grid, ctx->stream, d_descA, row_begin, row_end, d_descB, n2, split_size, order, pb, ps, pi);
+    VO_CHECK_LAUNCH(ctx, "match_scan_kernel");
+  }
   match_merge_kernel<<<(unsigned)merge_blocks, 256, 0, ctx->stream>>>(pb, ps, pi, rows, (int)n_splits, dist_thr,
                                                                       ratio_thr, d_best, d_second, idx, flags,
                                                                       counts);

@@ -53,6 +53,24 @@ def test_match_bit_exact(ctx, oracle, n1, n2, dim):
     assert np.array_equal(second.view(np.uint32), rsecond.view(np.uint32))
 
 
+@pytest.mark.parametrize("n1,n2,noise,dup", [(8192, 8192, 0.0, 0.02), (9001, 12345, 0.1, 0.0), (20000, 8200, 0.14, 0.3)])
+def test_match_indexed_path_bit_exact(ctx, oracle, n1, n2, noise, dup):
+    """both sets >= 8192 rows: Morton-ordered rows AND columns, tile boxes, tile skipping, out-of-order column
+    visits with the explicit lowest-index tie-break (many duplicate columns) - still bit-exact"""
+    A, B = synth.descriptors(n1, n2, seed=n1 + n2, copy_frac=0.8, dup_frac=dup, noise=noise)
+    rp, rstats, rbest, rsecond, ridx = oracle.match(A, B, want_rows=True, n_threads=8)
+    p2, best, second, idx = _rows_dev(ctx, A, B)
+    assert np.array_equal(idx, ridx)
+    assert np.array_equal(best.view(np.uint32), rbest.view(np.uint32))
+    assert np.array_equal(second.view(np.uint32), rsecond.view(np.uint32))
+    assert np.array_equal(p2, rp)
+    # a row shard takes the same path and concatenates
+    lo = max(0, min(n1 // 3, n1 - 8500))
+    hi = min(n1, lo + 8500)
+    ps, _, _, _ = _rows_dev(ctx, A, B, lo, hi)
+    assert np.array_equal(ps, rp[(rp[:, 0] >= lo) & (rp[:, 0] < hi)])
+
+
 def test_match_noisy_and_threshold_edge(ctx, oracle):
     """noise puts many best distances near 0.2 and ratios near 0.8: exact rounding decides"""
     A, B = synth.descriptors(4000, 6000, seed=9, copy_frac=0.7, noise=0.14)
