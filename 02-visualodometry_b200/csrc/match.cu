@@ -25,8 +25,16 @@
 
 namespace {
 
-constexpr int kMatchThreads = 128;
-constexpr int kTileRows = 256;  // rows of B per shared-memory tile
+#ifndef VO_MATCH_THREADS
+#define VO_MATCH_THREADS 32
+#endif
+#ifndef VO_MATCH_TILE
+#define VO_MATCH_TILE 128
+#endif
+// rows per CTA / columns per tile, measured on B200 for the indexed scan (exp/match_time.py, 1M x 1M and 131072 x 1M, ms):
+// 128/256: 161 / 44.9   64/256: 134 / 43.6   64/128: 133 / 45.4   32/256: 145 / 40.7   32/128: 133 / 40.2
+constexpr int kMatchThreads = VO_MATCH_THREADS;
+constexpr int kTileRows = VO_MATCH_TILE;  // rows of B per shared-memory tile
 constexpr int kMaxDim = 16;
 
 template <int DIM>
@@ -671,7 +679,7 @@ int vo_match_dev(vo_ctx* ctx, const float* d_descA, int64_t n1, const float* d_d
 
   // column splits: fill whole waves (sm_count * resident CTAs) without starving any CTA of work
   const long long row_blocks = (rows + kMatchThreads - 1) / kMatchThreads;
-  const long long slots = (long long)ctx->sm_count * 8;
+  const long long slots = (long long)ctx->sm_count * 32;
   long long n_splits = 1;
   if (row_blocks < 2 * slots && n2 > 0) {
     n_splits = (2 * slots + row_blocks - 1) / row_blocks;
