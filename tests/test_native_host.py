@@ -44,6 +44,57 @@ def test_native_vo_driver(dataset, tmp_path):
     assert "Number of duplicate world points" in r.stdout
 
 
+SELFTEST = os.path.join(ROOT, "02-visualodometry_b200", "host", "host_selftest")
+
+
+def test_host_mirror_logic_on_cpu(dataset, tmp_path, oracle):
+    """the host mirror's own code (loaders of src/my_utilities.cpp:20-182, gathers, augment_pose, umeyama scale,
+    compute_scale, computeRotationError, the inline Camera::projectPoint, Iso3f algebra) against numpy / the oracle.
+    Runs without a GPU."""
+    prefix = dataset_io.write_meas_files(dataset, str(tmp_path / "data"))
+    world = tmp_path / "world.dat"
+    rng = np.random.default_rng(0)
+    W = np.concatenate([rng.uniform(-10, 10, (50, 3)), rng.uniform(-1, 1, (50, 10))], 1).astype(np.float32)
+    with open(world, "w") as f:
+        for i, row in enumerate(W):
+            f.write("%d %s\n" % (i % 40, " ".join("%.9g" % x for x in row)))  # ids 0..9 appear twice
+    r = subprocess.run([SELFTEST, prefix, "121", str(world)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    out = {l.split()[0]: l.split()[1:] for l in r.stdout.splitlines() if l and l.split()[0] in
+           ("frames", "seq_last", "split", "v2", "augment", "umeyama_scale", "project", "world")}
+    ds = dataset
+    assert out["frames"][0] == "121" and out["frames"][2] == str(len(ds["uv"]))
+    assert abs(float(out["frames"][4]) - ds["uv"].astype(np.float64).sum()) < 1e-3
+    assert abs(float(out["frames"][6]) - ds["desc"].astype(np.float64).sum()) < 1e-4
+    assert int(out["frames"][8]) == int(ds["id_real"].astype(np.int64).sum() + 3 * ds["id_meas"].astype(np.int64).sum())
+    assert out["seq_last"][0] == "120"
+    assert np.array_equal(np.array(out["seq_last"][2:5], np.float64).astype(np.float32), ds["gt_pose"][120])
+    assert np.array_equal(np.array(out["seq_last"][6:9], np.float64).astype(np.float32), ds["odom_pose"][120])
+    assert out["split"] == ["5", "point", "12", "-1e-3"]
+    f0 = replay.frame(ds, 0)
+    assert out["v2"][0] == str(len(f0["uv"])) and np.float32(out["v2"][1]) == f0["uv"][0, 0] and np.float32(out["v2"][2]) == f0["uv"][-1, 1]
+    G = replay.augment_pose(ds["gt_pose"][120])
+    assert np.allclose([float(x) for x in out["augment"][:4]], [G[0, 0], G[0, 1], G[0, 3], G[1, 3]], atol=1e-6)
+    Gi = oracle.pose_inverse(G.astype(np.float32))
+    assert np.allclose([float(x) for x in out["augment"][5:7]], [Gi[0, 3], Gi[1, 3]], atol=1e-5)
+    # umeyama scale (Eigen::umeyama with scaling), mean-ratio scale, geodesic rotation error
+    odo = np.stack([replay.augment_pose(p)[:, 3] for p in ds["odom_pose"]]) * np.float32(0.37)
+    gt = np.stack([replay.augment_pose(p)[:, 3] for p in ds["gt_pose"]])
+    assert abs(float(out["umeyama_scale"][0]) - replay.umeyama_scale(odo, gt)) < 1e-4
+    na, nb = np.linalg.norm(odo, axis=1), np.linalg.norm(gt, axis=1)
+    ok = (na > 0) & (nb > 0)
+    assert abs(float(out["umeyama_scale"][2]) - (nb[ok] / na[ok]).mean()) < 1e-4
+    dth = ds["odom_pose"][120, 2] - ds["gt_pose"][120, 2]
+    assert abs(float(out["umeyama_scale"][4]) - abs(dth)) < 1e-4
+    # Camera::projectPoint == the oracle's restatement of src/camera.h:24-36, point for point
+    i = np.arange(1000, dtype=np.float32)
+    pts = np.stack([np.float32(0.013) * i - np.float32(6), np.float32(0.007) * i - np.float32(3), np.float32(0.02) * i - np.float32(4)], 1)
+    uv, inside = oracle.project_points(replay.K_REF, 480, 640, G.astype(np.float32), pts, False)
+    assert int(out["project"][1]) == inside
+    assert abs(float(out["project"][3]) - (uv[:, 0].astype(np.float64) + 2.0 * uv[:, 1]).sum()) < 1e-2
+    assert out["world"][0] == "50" and out["world"][4] == "10"
+
+
 def test_native_refuses_to_run_without_gpu(dataset, tmp_path):
     """no CPU fallback: without a device the process must fail loudly, not produce output files"""
     vo = backends.product()
