@@ -613,6 +613,12 @@ __global__ void __launch_bounds__(256) picp_pack_kernel(const int2* __restrict__
   pk[4 * stride + i] = z.y;
 }
 
+struct PoseArg { float p[12]; };
+// the pose travels as a kernel argument: no staging buffer, no host synchronisation
+__global__ void picp_set_pose_kernel(PicpDev* dev, PoseArg pose) {
+  if (threadIdx.x < 12) dev->pose[threadIdx.x] = pose.p[threadIdx.x];
+}
+
 __global__ void picp_reset_kernel(PicpDev* dev, float rel_tol) {
   dev->round = 0;
   dev->stop = 0;
@@ -825,13 +831,10 @@ int vo_picp_set_pose(vo_picp* s, const float pose[12]) {
   if (!s || !pose) return VO_ERR_INVALID;
   int st = vo_ctx_activate(s->ctx);
   if (st) return st;
-  void* h;
-  st = vo_pinned(s->ctx, 64, &h);
-  if (st) return st;
-  VO_CUDA(s->ctx, cudaStreamSynchronize(s->ctx->stream));  // the staging buffer may still be in flight
-  memcpy(h, pose, 12 * sizeof(float));
-  VO_CUDA(s->ctx, cudaMemcpyAsync(s->d_dev, h, 12 * sizeof(float), cudaMemcpyHostToDevice, s->ctx->stream));
-  VO_CUDA(s->ctx, cudaStreamSynchronize(s->ctx->stream));
+  PoseArg a;
+  memcpy(a.p, pose, sizeof(a.p));
+  picp_set_pose_kernel<<<1, 32, 0, s->ctx->stream>>>(s->d_dev, a);
+  VO_CHECK_LAUNCH(s->ctx, "picp_set_pose_kernel");
   return VO_OK;
 }
 
