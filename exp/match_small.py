@@ -1,0 +1,13 @@
+import importlib, sys, os, torch
+R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, R); sys.path.insert(0, os.path.join(R, "tests")); import synth
+vo = importlib.import_module("02-visualodometry_b200")
+ctx = vo.Context(0)
+n1, n2 = 8192, 1 << 20
+A, B = synth.descriptors(n1, n2, seed=42)
+dA, dB = torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda()
+pairs = torch.empty((n1, 2), dtype=torch.int32, device="cuda")
+for _ in range(2):
+    n, _ = ctx.match_dev(dA.data_ptr(), n1, dB.data_ptr(), n2, 10, pairs.data_ptr(), n1)
+torch.cuda.synchronize()
+print("matches", n)
