@@ -328,7 +328,17 @@ __global__ void __launch_bounds__(kTileRows) match_tilebox10_kernel(const float*
   }
 }
 
-constexpr int kSuper = 16;  // tiles per super-tile (second level of the box hierarchy)
+#ifndef VO_MATCH_SUPER
+#define VO_MATCH_SUPER 16
+#endif
+constexpr int kSuper = VO_MATCH_SUPER;  // tiles per super-tile (second level of the box hierarchy)
+
+#ifdef VO_MATCH_COUNTERS  // exp/ builds only: how much of the column set the indexed scan really touches
+__device__ unsigned long long g_match_counters[4];  // super-tiles entered, tiles scanned, pair records finished, pair records bounded
+#define VO_COUNT(i, n) do { if (threadIdx.x == 0) atomicAdd(&g_match_counters[i], (unsigned long long)(n)); } while (0)
+#else
+#define VO_COUNT(i, n) do { } while (0)
+#endif
 
 __global__ void match_superbox10_kernel(const float* __restrict__ box, long long n_tiles, float* __restrict__ sbox) {
   const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -358,47 +368,49 @@ __device__ __forceinline__ void update_best_tie(float d, int j, float& best, flo
   best = lt ? d : best;
 }
 
-// Scan with tile skipping. A CTA owns 128 Morton-adjacent query rows; it walks the column tiles outward from its
-// own position on the curve and skips a tile when the squared distance between its rows' box and the tile's box
-// (in the lower-bound dimensions) cannot be below any row's current second-best.
+// Scan with tile skipping. A CTA owns 32 Morton-adjacent query rows (lane = row) and `n_warps` warps that all hold
+// the same rows; the column super-tiles are visited outward from the rows' own position on the curve, warp w taking
+// every n_warps-th super-tile of that order.  A (super-)tile is skipped when, for every row, the squared distance
+// from the row's point to the tile's box (in the lower-bound dimensions) exceeds the row's second-best bound.
 //   exactness: lb_float(row, col) >= lb_real * (1 - 4 ulp) >= box_real * (1 - 4 ulp) > box_float * (1 - 1e-5),
-//   so box_float * (1 - 1e-5) >= second  =>  lb_float >= second  =>  the column cannot change the row's result.
-__global__ void __launch_bounds__(kMatchThreads) match_scan10_indexed_kernel(
+//   so box_float * (1 - 1e-5) > bound  =>  d >= lb_float > bound >= final second >= final best: the column can
+//   change neither value nor (being strictly farther than the best) the lowest-index tie rule.
+//   `bound` = min(own second, s_bound[row]); s_bound is the smallest second-best any warp of the CTA has published:
+//   a second-best over a subset of the columns is never below the second-best over all of them.
+// The warps never synchronise with one another until the final merge (tile buffers are per warp).
+// n_warps > 1 is for row counts too small to fill the machine with one warp per 32 rows: a single warp per scheduler
+// runs this loop latency-bound (measured 18 ms for 8192 x 1M rows with 256 lone warps).
+constexpr int kTileBytes = (kTileRows / 2) * kPairFloats * 4 + kTileRows * 4;  // pair records + original indices
+constexpr int kMaxScanWarps = 16;
+
+#ifndef VO_SCAN_MINB
+#define VO_SCAN_MINB 1
+#endif
+__global__ void __launch_bounds__(32 * kMaxScanWarps, VO_SCAN_MINB) match_scan10_indexed_kernel(
     const float* __restrict__ A, long long row_begin, long long rows, const unsigned* __restrict__ row_order,
     const unsigned* __restrict__ row_keys_sorted, const float* __restrict__ rec, const int* __restrict__ orig,
     const float* __restrict__ box, const float* __restrict__ sbox, const unsigned* __restrict__ col_keys_sorted,
-    long long n2, float* __restrict__ o_best, float* __restrict__ o_second, int* __restrict__ o_idx) {
+    long long n2, const int* __restrict__ range_flag, float* __restrict__ o_best, float* __restrict__ o_second,
+    int* __restrict__ o_idx) {
+  if (*range_flag == 0) return;  // the tensor-core filtered scan (below) handles this call
   constexpr int DIM = 10;
-  __shared__ __align__(16) float sB[(kTileRows / 2) * kPairFloats];
-  __shared__ int sOrig[kTileRows];
-  __shared__ float s_lo[kMatchThreads / 32][4], s_hi[kMatchThreads / 32][4];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ long long s_t0;
-  const long long slot = (long long)blockIdx.x * kMatchThreads + threadIdx.x;
+  __shared__ int s_bound[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+  float* sB = reinterpret_cast<float*>(smem_raw + (size_t)warp * kTileBytes);
+  int* sOrig = reinterpret_cast<int*>(sB + (kTileRows / 2) * kPairFloats);
+  const long long slot = (long long)blockIdx.x * 32 + lane;
   const bool valid = slot < rows;
   const long long r = valid ? (long long)row_order[slot] : 0;
   f2 a[DIM];
-  float lo[4], hi[4];
 #pragma unroll
   for (int k = 0; k < DIM; ++k) {
     const float v = valid ? __ldg(A + (row_begin + r) * DIM + k) : NAN;
     a[dim_slot10(k)] = pack2(v, v);
   }
-#pragma unroll
-  for (int d = 0; d < 4; ++d) {
-    float v, w;
-    unpack2(a[d], v, w);
-    lo[d] = hi[d] = v;
-    for (int o = 16; o > 0; o >>= 1) {
-      lo[d] = fminf(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], o));
-      hi[d] = fmaxf(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], o));
-    }
-    if ((threadIdx.x & 31) == 0) {
-      s_lo[threadIdx.x >> 5][d] = lo[d];
-      s_hi[threadIdx.x >> 5][d] = hi[d];
-    }
-  }
   if (threadIdx.x == 0) {  // where this CTA's rows sit among the sorted columns
-    const long long mid = min(slot + kMatchThreads / 2, rows - 1);
+    const long long mid = min((long long)blockIdx.x * 32 + 16, rows - 1);
     const unsigned key = row_keys_sorted[mid];
     long long a0 = 0, a1 = n2;
     while (a0 < a1) {
@@ -408,25 +420,17 @@ __global__ void __launch_bounds__(kMatchThreads) match_scan10_indexed_kernel(
     }
     s_t0 = min(a0, n2 - 1) / (kTileRows * kSuper);  // home super-tile
   }
+  if (threadIdx.x < 32) s_bound[threadIdx.x] = __float_as_int(FLT_MAX);
   __syncthreads();
-#pragma unroll
-  for (int d = 0; d < 4; ++d) {
-    lo[d] = s_lo[0][d];
-    hi[d] = s_hi[0][d];
-    for (int w = 1; w < kMatchThreads / 32; ++w) {
-      lo[d] = fminf(lo[d], s_lo[w][d]);
-      hi[d] = fmaxf(hi[d], s_hi[w][d]);
-    }
-  }
-  float best = FLT_MAX, second = FLT_MAX;
+  float best = FLT_MAX, second = FLT_MAX, bound = FLT_MAX;
   int idx = -1;
   const long long n_tiles = (n2 + kTileRows - 1) / kTileRows;
   const long long n_super = (n_tiles + kSuper - 1) / kSuper;
-  // Can any row of this CTA still be improved by a column inside box i?  Per lane: squared distance from the
-  // lane's own point to the box (in the lower-bound dimensions), shrunk by the rounding margin, against the lane's
-  // own second-best.  (One box around all rows of the CTA would be useless for the CTAs that straddle a jump of
-  // the curve: they would walk every tile. Measured: 127 ms -> 101 ms at 1M x 1M, 40 -> 26 ms at 131072 x 1M.
-  // Visiting the tiles in rings of increasing box distance instead of curve order was measured slower: 171 ms.)
+  const long long home = s_t0, n_up = n_super - home, n_both = min(home, n_up);
+  // Per lane: squared distance from the lane's own point to the box, shrunk by the rounding margin, against the
+  // lane's bound.  (One box around all rows of the CTA is useless for the CTAs that straddle a jump of the curve:
+  // they would walk every tile. Measured: 127 ms -> 101 ms at 1M x 1M, 40 -> 26 ms at 131072 x 1M.  Visiting the
+  // tiles in rings of increasing box distance instead of curve order was measured slower: 171 ms.)
   float pt[4];
 #pragma unroll
   for (int d = 0; d < 4; ++d) {
@@ -437,66 +441,359 @@ __global__ void __launch_bounds__(kMatchThreads) match_scan10_indexed_kernel(
     const float4 bl = __ldg(reinterpret_cast<const float4*>(bx) + 2 * i), bh = __ldg(reinterpret_cast<const float4*>(bx) + 2 * i + 1);
     const float g0 = fmaxf(0.f, fmaxf(bl.x - pt[0], pt[0] - bh.x)), g1 = fmaxf(0.f, fmaxf(bl.y - pt[1], pt[1] - bh.y));
     const float g2 = fmaxf(0.f, fmaxf(bl.z - pt[2], pt[2] - bh.z)), g3 = fmaxf(0.f, fmaxf(bl.w - pt[3], pt[3] - bh.w));
-    const float bound = (g0 * g0 + g1 * g1 + g2 * g2 + g3 * g3) * 0.99999f;
-    return __syncthreads_or(valid && !(bound >= second)) != 0;  // NaN bounds never skip
+    const float bb = (g0 * g0 + g1 * g1 + g2 * g2 + g3 * g3) * 0.99999f;
+    return __any_sync(0xffffffffu, valid && !(bb > bound));  // NaN bounds never skip
   };
-  long long up = s_t0, down = s_t0 - 1;
-  for (long long step = 0; step < n_super; ++step) {
+  for (long long step = warp; step < n_super; step += n_warps) {
+    // step -> super-tile: home, home-1, home+1, home-2, ... then the rest of the longer side
     long long g;
-    if ((step & 1) == 0) g = (up < n_super) ? up++ : down--;
-    else g = (down >= 0) ? down-- : up++;
+    if (step < 2 * n_both) g = (step & 1) ? home - ((step + 1) >> 1) : home + (step >> 1);
+    else g = (n_up > home) ? home + (step - n_both) : home - 1 - (step - n_both);
+    if (n_warps > 1) bound = fminf(second, __int_as_float(s_bound[lane]));
     if (!box_can_matter(sbox, g)) continue;  // 16 tiles at once
+    VO_COUNT(0, 1);
     const long long t_end = min(n_tiles, (g + 1) * kSuper);
     for (long long t = g * kSuper; t < t_end; ++t) {
-    if (!box_can_matter(box, t)) continue;
-    const long long j0 = t * kTileRows;
-    const int cnt = (int)((n2 - j0 < kTileRows) ? (n2 - j0) : kTileRows);
-    const int n_pairs = (cnt + 1) >> 1;
+      if (!box_can_matter(box, t)) continue;
+      VO_COUNT(1, 1);
+      const long long j0 = t * kTileRows;
+      const int cnt = (int)((n2 - j0 < kTileRows) ? (n2 - j0) : kTileRows);
+      const int n_pairs = (cnt + 1) >> 1;
+      __syncwarp();
+      {
+        const float4* src = reinterpret_cast<const float4*>(rec + (j0 >> 1) * kPairFloats);
+        float4* dst = reinterpret_cast<float4*>(sB);
+        for (int q = lane; q < n_pairs * (kPairFloats / 4); q += 32) dst[q] = __ldg(src + q);
+        for (int q = lane; q < 2 * n_pairs; q += 32) sOrig[q] = __ldg(orig + j0 + q);
+      }
+      __syncwarp();
+      auto lower_bound = [&](const float4* rc) {
+        const float4 v0 = rc[0], v1 = rc[1];
+        const f2 x0 = sq2(pack2(v0.x, v0.y), a[0]), x4 = sq2(pack2(v0.z, v0.w), a[1]);
+        const f2 x2 = sq2(pack2(v1.x, v1.y), a[2]), x6 = sq2(pack2(v1.z, v1.w), a[3]);
+        return add2(add2(x0, x4), add2(x2, x6));
+      };
+      auto finish = [&](const float4* rc, f2 lb, int p) {
+        const float4 v2 = rc[2], v3 = rc[3], v4 = rc[4];
+        const f2 x1 = sq2(pack2(v2.x, v2.y), a[4]), x5 = sq2(pack2(v2.z, v2.w), a[5]);
+        const f2 x3 = sq2(pack2(v3.x, v3.y), a[6]), x7 = sq2(pack2(v3.z, v3.w), a[7]);
+        const f2 x8 = sq2(pack2(v4.x, v4.y), a[8]), x9 = sq2(pack2(v4.z, v4.w), a[9]);
+        f2 d = add2(lb, add2(add2(x1, x5), add2(x3, x7)));
+        d = add2(add2(d, x8), x9);
+        float d0, d1;
+        unpack2(d, d0, d1);
+        // most finished distances still change nothing: only then touch the index table and the running triple
+        if (!__any_sync(0xffffffffu, (d0 <= bound) || (d1 <= bound))) return;
+        update_best_tie(d0, sOrig[2 * p], best, second, idx);
+        if (2 * p + 1 < cnt) update_best_tie(d1, sOrig[2 * p + 1], best, second, idx);
+        bound = fminf(bound, second);
+      };
+      auto may_improve = [&](f2 lb) {
+        float lb0, lb1;
+        unpack2(lb, lb0, lb1);
+        return __any_sync(0xffffffffu, (lb0 <= bound) || (lb1 <= bound));
+      };
+      int p = 0;
+      for (; p + 2 <= n_pairs; p += 2) {
+        const float4* recA = reinterpret_cast<const float4*>(sB + p * kPairFloats);
+        const float4* recB = reinterpret_cast<const float4*>(sB + (p + 1) * kPairFloats);
+        const f2 lbA = lower_bound(recA), lbB = lower_bound(recB);
+        const bool mA = may_improve(lbA), mB = may_improve(lbB);
+        VO_COUNT(2, (int)mA + (int)mB);
+        if (mA) finish(recA, lbA, p);
+        if (mB) finish(recB, lbB, p + 1);
+      }
+      if (p < n_pairs) {
+        const float4* rc = reinterpret_cast<const float4*>(sB + p * kPairFloats);
+        const f2 lb = lower_bound(rc);
+        if (may_improve(lb)) finish(rc, lb, p);
+      }
+      VO_COUNT(3, n_pairs);
+      if (n_warps > 1) {  // publish / pick up the CTA-wide bound once per scanned tile
+        if (second < FLT_MAX) atomicMin(&s_bound[lane], __float_as_int(second));  // second >= 0: int order = float order
+        bound = fminf(second, __int_as_float(s_bound[lane]));
+      }
+    }
+  }
+  if (n_warps > 1) {
+    // merge the warps' triples: the bests through the tie-aware rule (their indices decide ties), the seconds as
+    // plain values (the column behind a warp's second has a higher index than that warp's best at equal distance)
     __syncthreads();
-    {
-      const float4* src = reinterpret_cast<const float4*>(rec + (j0 >> 1) * kPairFloats);
-      float4* dst = reinterpret_cast<float4*>(sB);
-      for (int q = threadIdx.x; q < n_pairs * (kPairFloats / 4); q += kMatchThreads) dst[q] = __ldg(src + q);
-      for (int q = threadIdx.x; q < 2 * n_pairs; q += kMatchThreads) sOrig[q] = __ldg(orig + j0 + q);
-    }
+    float* m_best = reinterpret_cast<float*>(smem_raw);
+    float* m_second = m_best + 32 * kMaxScanWarps;
+    int* m_idx = reinterpret_cast<int*>(m_second + 32 * kMaxScanWarps);
+    m_best[warp * 32 + lane] = best;
+    m_second[warp * 32 + lane] = second;
+    m_idx[warp * 32 + lane] = idx;
     __syncthreads();
-    auto lower_bound = [&](const float4* rc) {
-      const float4 v0 = rc[0], v1 = rc[1];
-      const f2 x0 = sq2(pack2(v0.x, v0.y), a[0]), x4 = sq2(pack2(v0.z, v0.w), a[1]);
-      const f2 x2 = sq2(pack2(v1.x, v1.y), a[2]), x6 = sq2(pack2(v1.z, v1.w), a[3]);
-      return add2(add2(x0, x4), add2(x2, x6));
-    };
-    auto finish = [&](const float4* rc, f2 lb, int p) {
-      const float4 v2 = rc[2], v3 = rc[3], v4 = rc[4];
-      const f2 x1 = sq2(pack2(v2.x, v2.y), a[4]), x5 = sq2(pack2(v2.z, v2.w), a[5]);
-      const f2 x3 = sq2(pack2(v3.x, v3.y), a[6]), x7 = sq2(pack2(v3.z, v3.w), a[7]);
-      const f2 x8 = sq2(pack2(v4.x, v4.y), a[8]), x9 = sq2(pack2(v4.z, v4.w), a[9]);
-      f2 d = add2(lb, add2(add2(x1, x5), add2(x3, x7)));
-      d = add2(add2(d, x8), x9);
-      float d0, d1;
-      unpack2(d, d0, d1);
-      update_best_tie(d0, sOrig[2 * p], best, second, idx);
-      if (2 * p + 1 < cnt) update_best_tie(d1, sOrig[2 * p + 1], best, second, idx);
-    };
-    auto may_improve = [&](f2 lb) {
-      float lb0, lb1;
-      unpack2(lb, lb0, lb1);
-      return __any_sync(0xffffffffu, (lb0 < second) || (lb1 < second));
-    };
-    int p = 0;
-    for (; p + 2 <= n_pairs; p += 2) {
-      const float4* recA = reinterpret_cast<const float4*>(sB + p * kPairFloats);
-      const float4* recB = reinterpret_cast<const float4*>(sB + (p + 1) * kPairFloats);
-      const f2 lbA = lower_bound(recA), lbB = lower_bound(recB);
-      if (may_improve(lbA)) finish(recA, lbA, p);
-      if (may_improve(lbB)) finish(recB, lbB, p + 1);
+    if (warp != 0) return;
+    best = second = FLT_MAX;
+    idx = -1;
+    float s_min = FLT_MAX;
+    for (int w = 0; w < n_warps; ++w) {
+      if (m_idx[w * 32 + lane] >= 0) update_best_tie(m_best[w * 32 + lane], m_idx[w * 32 + lane], best, second, idx);
+      s_min = fminf(s_min, m_second[w * 32 + lane]);
     }
-    if (p < n_pairs) {
-      const float4* rc = reinterpret_cast<const float4*>(sB + p * kPairFloats);
-      const f2 lb = lower_bound(rc);
-      if (may_improve(lb)) finish(rc, lb, p);
+    second = fminf(second, s_min);
+  }
+  if (valid) {
+    o_best[r] = best;
+    o_second[r] = second;
+    o_idx[r] = idx;
+  }
+}
+
+// ---- tensor-core distance filter (D = 10, indexed path) --------------------------------------------------------
+// The scan above spends ~40 issue slots per (32 rows x 2 columns) and finds that all but a handful of columns per
+// row are farther than the row's second-best.  Deciding THAT does not need the reference's float evaluation order:
+// a guaranteed lower bound of the distance is enough, and ||a-b||^2 = |a|^2 + |b|^2 - 2 a.b is one K = 16 bf16 MMA
+// per 16 rows x 8 columns (mma.sync m16n8k16: the accumulators land in registers, which is what a compare-only
+// epilogue wants; a TMEM round trip per K = 16 tile would be read-bandwidth bound).
+//   k = 0..9 : -2 bf16(a_k)        x  bf16(b_k)
+//   k = 10,11: hi, lo of (1-eps)|a|^2  x  1
+//   k = 12,13: 1                    x  hi, lo of (1-eps)|b|^2
+//   v = (1-eps)(|a|^2+|b|^2) - 2 sum bf16(a_k) bf16(b_k)   (+ accumulation error)
+// bf16 rounding: |bf16(x) - x| <= 2^-9 |x|, so 2 |sum a^b^ - sum ab| <= (2^-8 + 2^-18) sum 2|a_k b_k|
+// <= (2^-8 + 2^-18)(|a|^2 + |b|^2); hi/lo split, fp32 norm and accumulator errors are < 2^-15 (|a|^2+|b|^2); the float
+// evaluation of the reference is within 2^-19 of the real distance.  With eps = 2^-8 + 2^-12 that gives
+//   v < d_reference      for every finite pair whose magnitudes pass match_range_check_kernel (no overflow of the
+//                        norms, no underflow of the products; otherwise the exact scan above runs instead),
+// so v > bound  =>  d > bound >= final second-best: the column cannot change the row's result (strict, ties safe).
+// Columns with v <= bound are marked in a per-row bit mask and evaluated exactly (reference order, fp32) by the
+// row's lane.  NaN/inf rows or columns give v = NaN/inf: never marked, exactly like `d < best` with a NaN/inf d.
+constexpr float kFilterEps = 0.00390625f + 0.000244140625f;  // 2^-8 + 2^-12
+constexpr float kFilterMaxAbs = 1e15f, kFilterMinAbs = 1e-15f;
+
+__device__ __forceinline__ unsigned bf16x2_rn(float lo, float hi) {
+  unsigned r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
+// the 16 bf16 of one point (natural dimension order), as 8 words: w[i] = (k = 2i, 2i+1)
+__device__ __forceinline__ void filter_words(const float v[10], bool is_row, unsigned w[8]) {
+  float n = 0.f;
+#pragma unroll
+  for (int k = 0; k < 10; ++k) n = fmaf(v[k], v[k], n);
+  n *= (1.f - kFilterEps);
+  const float hi = __uint_as_float(bf16x2_rn(n, 0.f) << 16);
+  const float lo = n - hi;
+  const float s = is_row ? -2.f : 1.f;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) w[i] = bf16x2_rn(s * v[2 * i], s * v[2 * i + 1]);
+  const unsigned ones = 0x3F803F80u, norm = bf16x2_rn(hi, lo);
+  w[5] = is_row ? norm : ones;
+  w[6] = is_row ? ones : norm;
+  w[7] = 0u;
+}
+
+__global__ void match_range_check_kernel(const float* __restrict__ x, long long n, int* __restrict__ flag) {
+  bool bad = false;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float a = fabsf(__ldg(x + i));
+    bad |= (a <= FLT_MAX) && ((a > kFilterMaxAbs) || (a != 0.f && a < kFilterMinAbs));
+  }
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
+}
+
+// per column (sorted position j, padded to whole tiles with NaN): uint2[4], entry t = words (t, t+4) = the
+// m16n8k16 B fragment of lane 4*(j%8)+t, so a warp's fragment load for 8 columns is one coalesced 256-byte read
+__global__ void match_gatherfrag10_kernel(const float* __restrict__ B, const unsigned* __restrict__ order, long long n2,
+                                          long long n_padded, uint4* __restrict__ frag) {
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_padded) return;
+  unsigned w[8];
+  if (j < n2) {
+    const long long src = order[j];
+    float v[10];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) v[k] = __ldg(B + src * 10 + k);
+    filter_words(v, false, w);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) w[i] = 0x7FC07FC0u;
+  }
+  frag[2 * j] = make_uint4(w[0], w[4], w[1], w[5]);
+  frag[2 * j + 1] = make_uint4(w[2], w[6], w[3], w[7]);
+}
+
+__device__ __forceinline__ void mma_bf16_16816(float c[4], const unsigned a[4], uint2 b) {
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+      : "=f"(c[0]), "=f"(c[1]), "=f"(c[2]), "=f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b.x), "r"(b.y), "f"(0.f));
+}
+
+// Same walk, same bounds and same merge as match_scan10_indexed_kernel; the per-tile work is the filter.
+__global__ void __launch_bounds__(32 * kMaxScanWarps) match_scan10_mma_kernel(
+    const float* __restrict__ A, long long row_begin, long long rows, const unsigned* __restrict__ row_order,
+    const unsigned* __restrict__ row_keys_sorted, const float* __restrict__ rec, const int* __restrict__ orig,
+    const uint2* __restrict__ frag, const float* __restrict__ box, const float* __restrict__ sbox,
+    const unsigned* __restrict__ col_keys_sorted, long long n2, const int* __restrict__ range_flag,
+    float* __restrict__ o_best, float* __restrict__ o_second, int* __restrict__ o_idx) {
+  if (*range_flag != 0) return;  // magnitudes outside the filter's error analysis: the exact scan runs instead
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ long long s_t0;
+  __shared__ int s_bound[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+  const int g = lane >> 2, tq = lane & 3;
+  unsigned* sA = reinterpret_cast<unsigned*>(smem_raw);                         // [32 rows][8 words]
+  unsigned* mask = reinterpret_cast<unsigned*>(smem_raw) + 256 + warp * 128;    // [32 rows][4 words] per warp
+  const long long slot = (long long)blockIdx.x * 32 + lane;
+  const bool valid = slot < rows;
+  const long long r = valid ? (long long)row_order[slot] : 0;
+  float a[10];  // slot order (pair-record order), fp32: the exact evaluation
+  {
+    float v[10];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) {
+      v[k] = valid ? __ldg(A + (row_begin + r) * 10 + k) : NAN;
+      a[dim_slot10(k)] = v[k];
     }
+    if (warp == 0) {
+      unsigned w[8];
+      filter_words(v, true, w);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sA[lane * 8 + i] = w[i];
     }
+  }
+  *reinterpret_cast<uint4*>(mask + lane * 4) = make_uint4(0, 0, 0, 0);
+  if (threadIdx.x == 0) {  // where this CTA's rows sit among the sorted columns
+    const long long mid = min((long long)blockIdx.x * 32 + 16, rows - 1);
+    const unsigned key = row_keys_sorted[mid];
+    long long a0 = 0, a1 = n2;
+    while (a0 < a1) {
+      const long long m = (a0 + a1) >> 1;
+      if (col_keys_sorted[m] < key) a0 = m + 1;
+      else a1 = m;
+    }
+    s_t0 = min(a0, n2 - 1) / (kTileRows * kSuper);  // home super-tile
+  }
+  if (threadIdx.x < 32) s_bound[threadIdx.x] = __float_as_int(FLT_MAX);
+  __syncthreads();
+  unsigned afrag[2][4];
+#pragma unroll
+  for (int mb = 0; mb < 2; ++mb) {
+    afrag[mb][0] = sA[(mb * 16 + g) * 8 + tq];
+    afrag[mb][1] = sA[(mb * 16 + g + 8) * 8 + tq];
+    afrag[mb][2] = sA[(mb * 16 + g) * 8 + tq + 4];
+    afrag[mb][3] = sA[(mb * 16 + g + 8) * 8 + tq + 4];
+  }
+  float best = FLT_MAX, second = FLT_MAX, bound = FLT_MAX;
+  int idx = -1;
+  float thr[4] = {FLT_MAX, FLT_MAX, FLT_MAX, FLT_MAX};  // bounds of rows g, g+8, g+16, g+24 (this thread's outputs)
+  auto refresh_thr = [&]() {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) thr[i] = __shfl_sync(0xffffffffu, bound, g + 8 * i);
+  };
+  const long long n_tiles = (n2 + kTileRows - 1) / kTileRows;
+  const long long n_super = (n_tiles + kSuper - 1) / kSuper;
+  const long long home = s_t0, n_up = n_super - home, n_both = min(home, n_up);
+  const float pt[4] = {a[0], a[1], a[2], a[3]};
+  auto box_can_matter = [&](const float* bx, long long i) {
+    const float4 bl = __ldg(reinterpret_cast<const float4*>(bx) + 2 * i), bh = __ldg(reinterpret_cast<const float4*>(bx) + 2 * i + 1);
+    const float g0 = fmaxf(0.f, fmaxf(bl.x - pt[0], pt[0] - bh.x)), g1 = fmaxf(0.f, fmaxf(bl.y - pt[1], pt[1] - bh.y));
+    const float g2 = fmaxf(0.f, fmaxf(bl.z - pt[2], pt[2] - bh.z)), g3 = fmaxf(0.f, fmaxf(bl.w - pt[3], pt[3] - bh.w));
+    const float bb = (g0 * g0 + g1 * g1 + g2 * g2 + g3 * g3) * 0.99999f;
+    return __any_sync(0xffffffffu, valid && !(bb > bound));  // NaN bounds never skip
+  };
+  static_assert(kTileRows == 128, "mask words / fragment indexing assume 128-column tiles");
+  for (long long step = warp; step < n_super; step += n_warps) {
+    long long sg;
+    if (step < 2 * n_both) sg = (step & 1) ? home - ((step + 1) >> 1) : home + (step >> 1);
+    else sg = (n_up > home) ? home + (step - n_both) : home - 1 - (step - n_both);
+    if (n_warps > 1) {
+      const float nb = fminf(second, __int_as_float(s_bound[lane]));
+      if (__any_sync(0xffffffffu, nb < bound)) {
+        bound = nb;
+        refresh_thr();
+      }
+    }
+    if (!box_can_matter(sbox, sg)) continue;  // 16 tiles at once
+    VO_COUNT(0, 1);
+    const long long t_end = min(n_tiles, (sg + 1) * kSuper);
+    for (long long t = sg * kSuper; t < t_end; ++t) {
+      if (!box_can_matter(box, t)) continue;
+      VO_COUNT(1, 1);
+      const uint2* fr = frag + (size_t)t * (kTileRows * 4) + lane;
+      uint2 b[16];
+#pragma unroll
+      for (int nb = 0; nb < 16; ++nb) b[nb] = __ldg(fr + nb * 32);
+#pragma unroll
+      for (int nb = 0; nb < 16; ++nb) {
+        float c[4], e[4];
+        mma_bf16_16816(c, afrag[0], b[nb]);
+        mma_bf16_16816(e, afrag[1], b[nb]);
+        const bool hit = (fminf(c[0], c[1]) <= thr[0]) | (fminf(c[2], c[3]) <= thr[1]) | (fminf(e[0], e[1]) <= thr[2]) |
+                         (fminf(e[2], e[3]) <= thr[3]);
+        if (hit) {
+          const int word = nb >> 2, sh = (nb & 3) * 8 + 2 * tq;
+          const unsigned m0 = (unsigned)(c[0] <= thr[0]) | ((unsigned)(c[1] <= thr[0]) << 1);
+          const unsigned m1 = (unsigned)(c[2] <= thr[1]) | ((unsigned)(c[3] <= thr[1]) << 1);
+          const unsigned m2 = (unsigned)(e[0] <= thr[2]) | ((unsigned)(e[1] <= thr[2]) << 1);
+          const unsigned m3 = (unsigned)(e[2] <= thr[3]) | ((unsigned)(e[3] <= thr[3]) << 1);
+          if (m0) atomicOr(&mask[(g) * 4 + word], m0 << sh);
+          if (m1) atomicOr(&mask[(g + 8) * 4 + word], m1 << sh);
+          if (m2) atomicOr(&mask[(g + 16) * 4 + word], m2 << sh);
+          if (m3) atomicOr(&mask[(g + 24) * 4 + word], m3 << sh);
+        }
+      }
+      __syncwarp();
+      const uint4 mk = *reinterpret_cast<const uint4*>(mask + lane * 4);
+      const bool mine = (mk.x | mk.y | mk.z | mk.w) != 0;
+      if (!__any_sync(0xffffffffu, mine)) continue;
+      if (mine) {
+        *reinterpret_cast<uint4*>(mask + lane * 4) = make_uint4(0, 0, 0, 0);
+        const unsigned words[4] = {mk.x, mk.y, mk.z, mk.w};
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          unsigned bits = words[w];
+          while (bits) {
+            const int bpos = __ffs(bits) - 1;
+            bits &= bits - 1;
+            const long long j = t * kTileRows + w * 32 + bpos;
+            const float* rc = rec + (j >> 1) * kPairFloats + (j & 1);
+            float q[10];
+#pragma unroll
+            for (int sI = 0; sI < 10; ++sI) {
+              const float df = __fsub_rn(__ldg(rc + 2 * sI), a[sI]);
+              q[sI] = __fmul_rn(df, df);
+            }
+            // my_utilities.h:85-91 in Eigen's reduction order (same tree as the packed scan)
+            float d = __fadd_rn(__fadd_rn(__fadd_rn(q[0], q[1]), __fadd_rn(q[2], q[3])),
+                                __fadd_rn(__fadd_rn(q[4], q[5]), __fadd_rn(q[6], q[7])));
+            d = __fadd_rn(__fadd_rn(d, q[8]), q[9]);
+            VO_COUNT(2, 0);
+            if (d <= bound) update_best_tie(d, __ldg(orig + j), best, second, idx);
+          }
+        }
+        bound = fminf(bound, second);
+      }
+      __syncwarp();
+      if (n_warps > 1) {
+        if (second < FLT_MAX) atomicMin(&s_bound[lane], __float_as_int(second));  // second >= 0: int order = float order
+        bound = fminf(bound, __int_as_float(s_bound[lane]));
+      }
+      refresh_thr();
+    }
+  }
+  if (n_warps > 1) {
+    __syncthreads();
+    float* m_best = reinterpret_cast<float*>(smem_raw);
+    float* m_second = m_best + 32 * n_warps;
+    int* m_idx = reinterpret_cast<int*>(m_second + 32 * n_warps);
+    m_best[warp * 32 + lane] = best;
+    m_second[warp * 32 + lane] = second;
+    m_idx[warp * 32 + lane] = idx;
+    __syncthreads();
+    if (warp != 0) return;
+    best = second = FLT_MAX;
+    idx = -1;
+    float s_min = FLT_MAX;
+    for (int w = 0; w < n_warps; ++w) {
+      if (m_idx[w * 32 + lane] >= 0) update_best_tie(m_best[w * 32 + lane], m_idx[w * 32 + lane], best, second, idx);
+      s_min = fminf(s_min, m_second[w * 32 + lane]);
+    }
+    second = fminf(second, s_min);
   }
   if (valid) {
     o_best[r] = best;
@@ -684,6 +981,17 @@ int vo_scan_block_counts(vo_ctx* ctx, int* d_counts, long long n_blocks, long lo
   return VO_OK;
 }
 
+#ifdef VO_MATCH_COUNTERS
+extern "C" int vo_debug_match_counters(unsigned long long out[4], int reset) {
+  if (cudaMemcpyFromSymbol(out, g_match_counters, 32) != cudaSuccess) return VO_ERR_CUDA;
+  if (reset) {
+    unsigned long long z[4] = {0, 0, 0, 0};
+    if (cudaMemcpyToSymbol(g_match_counters, z, 32) != cudaSuccess) return VO_ERR_CUDA;
+  }
+  return VO_OK;
+}
+#endif
+
 extern "C" {
 
 int vo_match_dev(vo_ctx* ctx, const float* d_descA, int64_t n1, const float* d_descB, int64_t n2, int dim,
@@ -760,6 +1068,7 @@ int vo_match_dev(vo_ctx* ctx, const float* d_descA, int64_t n1, const float* d_d
   const size_t o_box = carve(indexed ? (size_t)n_tiles * 32 : 0);
   const long long n_super = (n_tiles + kSuper - 1) / kSuper;
   const size_t o_sbox = carve(indexed ? (size_t)n_super * 32 : 0);
+  const size_t o_frag = carve(indexed ? (size_t)n_tiles * kTileRows * 32 : 0);
   char* base;
   st = vo_scratch(ctx, off, (void**)&base);
   if (st) return st;
@@ -816,8 +1125,32 @@ int vo_match_dev(vo_ctx* ctx, const float* d_descA, int64_t n1, const float* d_d
       float* sbox = (float*)(base + o_sbox);
       match_superbox10_kernel<<<(unsigned)((n_super + 127) / 128), 128, 0, ctx->stream>>>(box, n_tiles, sbox);
       VO_CHECK_LAUNCH(ctx, "match_superbox10_kernel");
-      match_scan10_indexed_kernel<<<(unsigned)row_blocks, kMatchThreads, 0, ctx->stream>>>(
-          d_descA, row_begin, rows, sorted_ids, keys2, rec, orig, box, sbox, ckeys2, n2, pb, ps, pi);
+      // warps per 32-row group: enough to give every SM ~32 warps when the rows alone cannot
+      const long long groups = (rows + 31) / 32;
+      int n_warps = 1;
+      while (n_warps < kMaxScanWarps && groups * n_warps * 2 <= (long long)ctx->sm_count * 32) n_warps *= 2;
+      // magnitudes the filter's error analysis does not cover select the exact scan (flag read on the device)
+      int* range_flag = (int*)(base + o_small + 32);
+      match_range_check_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(d_descA + row_begin * 10, rows * 10, range_flag);
+      VO_CHECK_LAUNCH(ctx, "match_range_check_kernel");
+      match_range_check_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(d_descB, n2 * 10, range_flag);
+      VO_CHECK_LAUNCH(ctx, "match_range_check_kernel");
+      uint2* frag = (uint2*)(base + o_frag);
+      match_gatherfrag10_kernel<<<(unsigned)((n_tiles * kTileRows + 255) / 256), 256, 0, ctx->stream>>>(
+          d_descB, corder, n2, n_tiles * kTileRows, (uint4*)frag);
+      VO_CHECK_LAUNCH(ctx, "match_gatherfrag10_kernel");
+      const size_t mma_smem = 1024 + (size_t)n_warps * 512;
+      static_assert(1024 + 512 >= 3 * 32 * 4, "merge arrays reuse the fragment / mask buffers");
+      match_scan10_mma_kernel<<<(unsigned)groups, 32 * n_warps, mma_smem, ctx->stream>>>(
+          d_descA, row_begin, rows, sorted_ids, keys2, rec, orig, frag, box, sbox, ckeys2, n2, range_flag, pb, ps, pi);
+      VO_CHECK_LAUNCH(ctx, "match_scan10_mma_kernel");
+      const size_t scan_smem = (size_t)n_warps * kTileBytes;
+      static_assert(kTileBytes >= 3 * 32 * 4, "merge arrays reuse the tile buffers");
+      if (scan_smem > 48 * 1024)
+        VO_CUDA(ctx, cudaFuncSetAttribute(match_scan10_indexed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          kMaxScanWarps * kTileBytes));
+      match_scan10_indexed_kernel<<<(unsigned)groups, 32 * n_warps, scan_smem, ctx->stream>>>(
+          d_descA, row_begin, rows, sorted_ids, keys2, rec, orig, box, sbox, ckeys2, n2, range_flag, pb, ps, pi);
       VO_CHECK_LAUNCH(ctx, "match_scan10_indexed_kernel");
     }
   }

@@ -53,11 +53,20 @@ def test_match_bit_exact(ctx, oracle, n1, n2, dim):
     assert np.array_equal(second.view(np.uint32), rsecond.view(np.uint32))
 
 
-@pytest.mark.parametrize("n1,n2,noise,dup", [(8192, 8192, 0.0, 0.02), (9001, 12345, 0.1, 0.0), (20000, 8200, 0.14, 0.3)])
-def test_match_indexed_path_bit_exact(ctx, oracle, n1, n2, noise, dup):
-    """both sets >= 8192 rows: Morton-ordered rows AND columns, tile boxes, tile skipping, out-of-order column
-    visits with the explicit lowest-index tie-break (many duplicate columns) - still bit-exact"""
+@pytest.mark.parametrize("n1,n2,noise,dup,scale", [
+    (8192, 8192, 0.0, 0.02, 1.0), (9001, 12345, 0.1, 0.0, 1.0), (20000, 8200, 0.14, 0.3, 1.0),
+    (40000, 9000, 0.0, 0.05, 1.0),    # two warps per 32-row group
+    (80000, 8192, 0.05, 0.1, 1.0),    # one warp per group (the large-problem configuration)
+    (9000, 9000, 0.05, 0.1, 37.5),    # descriptors far from unit scale: the filter's error bound is relative
+    (9000, 9000, 0.05, 0.1, 3e16),    # magnitudes outside the filter's analysis: exact scan selected on the device
+    (9000, 9000, 0.05, 0.1, 1e-17),
+])
+def test_match_indexed_path_bit_exact(ctx, oracle, n1, n2, noise, dup, scale):
+    """both sets >= 8192 rows: Morton-ordered rows AND columns, tile boxes, tile skipping, tensor-core lower-bound
+    filter + exact evaluation of the survivors, out-of-order column visits with the explicit lowest-index tie-break
+    (many duplicate columns) - still bit-exact, values and indices of every row"""
     A, B = synth.descriptors(n1, n2, seed=n1 + n2, copy_frac=0.8, dup_frac=dup, noise=noise)
+    A, B = (A * np.float32(scale)).astype(np.float32), (B * np.float32(scale)).astype(np.float32)
     rp, rstats, rbest, rsecond, ridx = oracle.match(A, B, want_rows=True, n_threads=8)
     p2, best, second, idx = _rows_dev(ctx, A, B)
     assert np.array_equal(idx, ridx)
@@ -69,6 +78,23 @@ def test_match_indexed_path_bit_exact(ctx, oracle, n1, n2, noise, dup):
     hi = min(n1, lo + 8500)
     ps, _, _, _ = _rows_dev(ctx, A, B, lo, hi)
     assert np.array_equal(ps, rp[(rp[:, 0] >= lo) & (rp[:, 0] < hi)])
+
+
+def test_match_indexed_path_nonfinite(ctx, oracle):
+    """NaN / inf descriptors inside the indexed path: a NaN or inf distance never wins (`d < best` is false),
+    on the filter exactly as in the reference loop"""
+    A, B = synth.descriptors(9000, 9500, seed=77, copy_frac=0.8, dup_frac=0.01, noise=0.02)
+    rng = np.random.default_rng(5)
+    A[rng.integers(0, len(A), 40), rng.integers(0, 10, 40)] = np.nan
+    B[rng.integers(0, len(B), 40), rng.integers(0, 10, 40)] = np.nan
+    A[rng.integers(0, len(A), 10), rng.integers(0, 10, 10)] = np.inf
+    B[rng.integers(0, len(B), 10), rng.integers(0, 10, 10)] = -np.inf
+    rp, _, rbest, rsecond, ridx = oracle.match(A, B, want_rows=True, n_threads=8)
+    p2, best, second, idx = _rows_dev(ctx, A, B)
+    assert np.array_equal(idx, ridx)
+    assert np.array_equal(best.view(np.uint32), rbest.view(np.uint32))
+    assert np.array_equal(second.view(np.uint32), rsecond.view(np.uint32))
+    assert np.array_equal(p2, rp)
 
 
 def test_match_noisy_and_threshold_edge(ctx, oracle):
