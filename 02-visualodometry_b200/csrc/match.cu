@@ -617,14 +617,40 @@ __global__ void match_gatherfrag10_kernel(const float* __restrict__ B, const uns
   frag[2 * j + 1] = make_uint4(w[2], w[6], w[3], w[7]);
 }
 
-__device__ __forceinline__ void mma_bf16_16816(float c[4], const unsigned a[4], uint2 b) {
-  asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
-      : "=f"(c[0]), "=f"(c[1]), "=f"(c[2]), "=f"(c[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b.x), "r"(b.y), "f"(0.f));
+// d = a x b + {c_lo, c_lo, c_hi, c_hi}: the accumulator rows g / g+8 start from one value each
+__device__ __forceinline__ void mma_bf16_16816(float d[4], const unsigned a[4], uint2 b, float c_lo, float c_hi) {
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%11,%11};"
+      : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b.x), "r"(b.y), "f"(c_lo), "f"(c_hi));
+}
+__device__ __forceinline__ float min3(float a, float b, float c) {  // FMNMX3; NaN operands are ignored
+  float r;
+  asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
 }
 
+#ifndef VO_MMA_BUFS
+#define VO_MMA_BUFS 1
+#endif
+constexpr int kFragBufs = VO_MMA_BUFS;             // tile fragment buffers per warp (TMA bulk copies in flight)
+constexpr int kFragTileBytes = kTileRows * 32;     // 128 columns x 16 bf16
+constexpr int kMmaWarpSmem = 2048 + kFragBufs * kFragTileBytes + 64;
+
+// my_utilities.h:85-91 for one column of a pair record (stride 2 floats), in Eigen's reduction order - the same
+// tree, the same single roundings as the packed scan (sq2 / add2)
+__device__ __forceinline__ float exact_sqdist10(const float* __restrict__ rc, const float (&a)[10]) {
+#define VO_Q(sI) ([&]() { const float df = __fsub_rn(__ldg(rc + 2 * (sI)), a[sI]); return __fmul_rn(df, df); })()
+  const float q0 = VO_Q(0), q1 = VO_Q(1), q2 = VO_Q(2), q3 = VO_Q(3), q4 = VO_Q(4);
+  const float q5 = VO_Q(5), q6 = VO_Q(6), q7 = VO_Q(7), q8 = VO_Q(8), q9 = VO_Q(9);
+#undef VO_Q
+  const float d = __fadd_rn(__fadd_rn(__fadd_rn(q0, q1), __fadd_rn(q2, q3)), __fadd_rn(__fadd_rn(q4, q5), __fadd_rn(q6, q7)));
+  return __fadd_rn(__fadd_rn(d, q8), q9);
+}
 // Same walk, same bounds and same merge as match_scan10_indexed_kernel; the per-tile work is the filter.
-__global__ void __launch_bounds__(32 * kMaxScanWarps) match_scan10_mma_kernel(
+#ifndef VO_MMA_LB
+#define VO_MMA_LB 32 * kMaxScanWarps
+#endif
+__global__ void __launch_bounds__(VO_MMA_LB) match_scan10_mma_kernel(
     const float* __restrict__ A, long long row_begin, long long rows, const unsigned* __restrict__ row_order,
     const unsigned* __restrict__ row_keys_sorted, const float* __restrict__ rec, const int* __restrict__ orig,
     const uint2* __restrict__ frag, const float* __restrict__ box, const float* __restrict__ sbox,
@@ -637,7 +663,18 @@ __global__ void __launch_bounds__(32 * kMaxScanWarps) match_scan10_mma_kernel(
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
   const int g = lane >> 2, tq = lane & 3;
   unsigned* sA = reinterpret_cast<unsigned*>(smem_raw);                         // [32 rows][8 words]
-  unsigned* mask = reinterpret_cast<unsigned*>(smem_raw) + 256 + warp * 128;    // [32 rows][4 words] per warp
+  unsigned char* my_smem = smem_raw + 1024 + warp * kMmaWarpSmem;
+  unsigned* mask = reinterpret_cast<unsigned*>(my_smem);            // [32 rows][4 words]: surviving columns of a tile
+  float4* sb_stage = reinterpret_cast<float4*>(my_smem + 512);      // boxes of the next 32 super-tiles of the walk
+  float4* tb_stage = reinterpret_cast<float4*>(my_smem + 1536);     // boxes of the 16 tiles of one super-tile
+  unsigned char* fbuf = my_smem + 2048;                             // [kFragBufs][4 KB] column fragments of a tile
+  unsigned long long* fbar = reinterpret_cast<unsigned long long*>(my_smem + 2048 + kFragBufs * kFragTileBytes);
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < kFragBufs; ++i) mbar_init(&fbar[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  unsigned fphase = 0;  // bit i: parity the next wait on buffer i expects
   const long long slot = (long long)blockIdx.x * 32 + lane;
   const bool valid = slot < rows;
   const long long r = valid ? (long long)row_order[slot] : 0;
@@ -680,100 +717,156 @@ __global__ void __launch_bounds__(32 * kMaxScanWarps) match_scan10_mma_kernel(
   }
   float best = FLT_MAX, second = FLT_MAX, bound = FLT_MAX;
   int idx = -1;
-  float thr[4] = {FLT_MAX, FLT_MAX, FLT_MAX, FLT_MAX};  // bounds of rows g, g+8, g+16, g+24 (this thread's outputs)
+  // minus the bounds of rows g, g+8, g+16, g+24 (this thread's outputs): they go into the MMA as the accumulator's
+  // starting value, so a column survives iff its output is <= 0 and eight outputs need one comparison.  (The
+  // bound joins the sum as one more term no larger than the others unless the column is far below it anyway.)
+  float nthr[4] = {-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};
   auto refresh_thr = [&]() {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) thr[i] = __shfl_sync(0xffffffffu, bound, g + 8 * i);
+    for (int i = 0; i < 4; ++i) nthr[i] = -__shfl_sync(0xffffffffu, bound, g + 8 * i);
   };
   const long long n_tiles = (n2 + kTileRows - 1) / kTileRows;
   const long long n_super = (n_tiles + kSuper - 1) / kSuper;
   const long long home = s_t0, n_up = n_super - home, n_both = min(home, n_up);
   const float pt[4] = {a[0], a[1], a[2], a[3]};
-  auto box_can_matter = [&](const float* bx, long long i) {
-    const float4 bl = __ldg(reinterpret_cast<const float4*>(bx) + 2 * i), bh = __ldg(reinterpret_cast<const float4*>(bx) + 2 * i + 1);
+  // boxes are staged through shared memory 32 at a time (one coalesced read instead of one L2 round trip per test)
+  auto box_can_matter = [&](const float4* bx) {
+    const float4 bl = bx[0], bh = bx[1];
     const float g0 = fmaxf(0.f, fmaxf(bl.x - pt[0], pt[0] - bh.x)), g1 = fmaxf(0.f, fmaxf(bl.y - pt[1], pt[1] - bh.y));
     const float g2 = fmaxf(0.f, fmaxf(bl.z - pt[2], pt[2] - bh.z)), g3 = fmaxf(0.f, fmaxf(bl.w - pt[3], pt[3] - bh.w));
     const float bb = (g0 * g0 + g1 * g1 + g2 * g2 + g3 * g3) * 0.99999f;
     return __any_sync(0xffffffffu, valid && !(bb > bound));  // NaN bounds never skip
   };
-  static_assert(kTileRows == 128, "mask words / fragment indexing assume 128-column tiles");
-  for (long long step = warp; step < n_super; step += n_warps) {
-    long long sg;
-    if (step < 2 * n_both) sg = (step & 1) ? home - ((step + 1) >> 1) : home + (step >> 1);
-    else sg = (n_up > home) ? home + (step - n_both) : home - 1 - (step - n_both);
-    if (n_warps > 1) {
-      const float nb = fminf(second, __int_as_float(s_bound[lane]));
-      if (__any_sync(0xffffffffu, nb < bound)) {
-        bound = nb;
-        refresh_thr();
-      }
-    }
-    if (!box_can_matter(sbox, sg)) continue;  // 16 tiles at once
-    VO_COUNT(0, 1);
-    const long long t_end = min(n_tiles, (sg + 1) * kSuper);
-    for (long long t = sg * kSuper; t < t_end; ++t) {
-      if (!box_can_matter(box, t)) continue;
-      VO_COUNT(1, 1);
-      const uint2* fr = frag + (size_t)t * (kTileRows * 4) + lane;
-      uint2 b[16];
-#pragma unroll
-      for (int nb = 0; nb < 16; ++nb) b[nb] = __ldg(fr + nb * 32);
-#pragma unroll
-      for (int nb = 0; nb < 16; ++nb) {
-        float c[4], e[4];
-        mma_bf16_16816(c, afrag[0], b[nb]);
-        mma_bf16_16816(e, afrag[1], b[nb]);
-        const bool hit = (fminf(c[0], c[1]) <= thr[0]) | (fminf(c[2], c[3]) <= thr[1]) | (fminf(e[0], e[1]) <= thr[2]) |
-                         (fminf(e[2], e[3]) <= thr[3]);
-        if (hit) {
-          const int word = nb >> 2, sh = (nb & 3) * 8 + 2 * tq;
-          const unsigned m0 = (unsigned)(c[0] <= thr[0]) | ((unsigned)(c[1] <= thr[0]) << 1);
-          const unsigned m1 = (unsigned)(c[2] <= thr[1]) | ((unsigned)(c[3] <= thr[1]) << 1);
-          const unsigned m2 = (unsigned)(e[0] <= thr[2]) | ((unsigned)(e[1] <= thr[2]) << 1);
-          const unsigned m3 = (unsigned)(e[2] <= thr[3]) | ((unsigned)(e[3] <= thr[3]) << 1);
-          if (m0) atomicOr(&mask[(g) * 4 + word], m0 << sh);
-          if (m1) atomicOr(&mask[(g + 8) * 4 + word], m1 << sh);
-          if (m2) atomicOr(&mask[(g + 16) * 4 + word], m2 << sh);
-          if (m3) atomicOr(&mask[(g + 24) * 4 + word], m3 << sh);
-        }
+  auto step_to_super = [&](long long step) {  // home, home-1, home+1, home-2, ... then the rest of the longer side
+    if (step < 2 * n_both) return (step & 1) ? home - ((step + 1) >> 1) : home + (step >> 1);
+    return (n_up > home) ? home + (step - n_both) : home - 1 - (step - n_both);
+  };
+  static_assert(kTileRows == 128 && kSuper == 16, "mask words / fragment / box staging assume 128-column tiles, 16 per super-tile");
+  const float4* box4 = reinterpret_cast<const float4*>(box);
+  const float4* sbox4 = reinterpret_cast<const float4*>(sbox);
+  for (long long step0 = warp; step0 < n_super; step0 += 32ll * n_warps) {
+    {  // the next 32 super-tile boxes of this warp's walk
+      const long long st = step0 + (long long)lane * n_warps;
+      float4 lo4 = make_float4(0, 0, 0, 0), hi4 = lo4;
+      if (st < n_super) {
+        const long long sgl = step_to_super(st);
+        lo4 = __ldg(sbox4 + 2 * sgl);
+        hi4 = __ldg(sbox4 + 2 * sgl + 1);
       }
       __syncwarp();
-      const uint4 mk = *reinterpret_cast<const uint4*>(mask + lane * 4);
-      const bool mine = (mk.x | mk.y | mk.z | mk.w) != 0;
-      if (!__any_sync(0xffffffffu, mine)) continue;
-      if (mine) {
-        *reinterpret_cast<uint4*>(mask + lane * 4) = make_uint4(0, 0, 0, 0);
-        const unsigned words[4] = {mk.x, mk.y, mk.z, mk.w};
+      sb_stage[2 * lane] = lo4;
+      sb_stage[2 * lane + 1] = hi4;
+      __syncwarp();
+    }
+    for (int si = 0; si < 32; ++si) {
+      const long long step = step0 + (long long)si * n_warps;
+      if (step >= n_super) break;
+      if (n_warps > 1) {
+        const float nb = fminf(second, __int_as_float(s_bound[lane]));
+        if (__any_sync(0xffffffffu, nb < bound)) {
+          bound = nb;
+          refresh_thr();
+        }
+      }
+      if (!box_can_matter(sb_stage + 2 * si)) continue;  // 16 tiles at once
+      VO_COUNT(0, 1);
+      const long long sg = step_to_super(step);
+      const long long t0 = sg * kSuper;
+      const int n_t = (int)min((long long)kSuper, n_tiles - t0);
+      __syncwarp();
+      tb_stage[lane] = (lane < 2 * n_t) ? __ldg(box4 + 2 * t0 + lane) : make_float4(0, 0, 0, 0);
+      __syncwarp();
+      // which of the 16 tiles can matter (current bounds); their fragments come through the TMA engine, the next
+      // needed tile's copy in flight while this one is filtered
+      unsigned need = 0;
+      for (int k = 0; k < n_t; ++k) need |= box_can_matter(tb_stage + 2 * k) ? (1u << k) : 0u;
+      if (!need) continue;
+      auto fetch = [&](int k, int buf) {
+        if (lane == 0) {
+          mbar_arrive_expect_tx(&fbar[buf], kFragTileBytes);
+          bulk_g2s(fbuf + buf * kFragTileBytes, frag + (size_t)(t0 + k) * (kTileRows * 4), kFragTileBytes, &fbar[buf]);
+        }
+      };
+      int k = __ffs(need) - 1, buf = 0;
+      need &= need - 1;
+      __syncwarp();  // every lane is done reading the buffers
+      fetch(k, 0);
+      while (k >= 0) {
+        int kn = -1;
+        if (kFragBufs > 1 && need) {
+          kn = __ffs(need) - 1;
+          need &= need - 1;
+          fetch(kn, buf ^ 1);
+        }
+        mbar_wait(&fbar[buf], (fphase >> buf) & 1u);
+        fphase ^= 1u << buf;
+        const long long t = t0 + k;
+        const uint2* fb = reinterpret_cast<const uint2*>(fbuf + buf * kFragTileBytes) + lane;
+        const int k_done = k;
+        if (kFragBufs > 1) {
+          k = kn;
+          buf ^= 1;
+        } else {
+          k = need ? __ffs(need) - 1 : -1;
+          need &= need - 1;
+        }
+        // the bounds may have tightened since the need mask was taken
+        if (!box_can_matter(tb_stage + 2 * k_done)) {
+          __syncwarp();
+          if (kFragBufs == 1 && k >= 0) fetch(k, 0);
+          continue;
+        }
+        VO_COUNT(1, 1);
 #pragma unroll
-        for (int w = 0; w < 4; ++w) {
-          unsigned bits = words[w];
-          while (bits) {
-            const int bpos = __ffs(bits) - 1;
-            bits &= bits - 1;
-            const long long j = t * kTileRows + w * 32 + bpos;
-            const float* rc = rec + (j >> 1) * kPairFloats + (j & 1);
-            float q[10];
-#pragma unroll
-            for (int sI = 0; sI < 10; ++sI) {
-              const float df = __fsub_rn(__ldg(rc + 2 * sI), a[sI]);
-              q[sI] = __fmul_rn(df, df);
-            }
-            // my_utilities.h:85-91 in Eigen's reduction order (same tree as the packed scan)
-            float d = __fadd_rn(__fadd_rn(__fadd_rn(q[0], q[1]), __fadd_rn(q[2], q[3])),
-                                __fadd_rn(__fadd_rn(q[4], q[5]), __fadd_rn(q[6], q[7])));
-            d = __fadd_rn(__fadd_rn(d, q[8]), q[9]);
-            VO_COUNT(2, 0);
-            if (d <= bound) update_best_tie(d, __ldg(orig + j), best, second, idx);
+        for (int nb = 0; nb < 16; ++nb) {
+          float c[4], e[4];
+          const uint2 bq = fb[nb * 32];
+          mma_bf16_16816(c, afrag[0], bq, nthr[0], nthr[1]);
+          mma_bf16_16816(e, afrag[1], bq, nthr[2], nthr[3]);
+          const float m = fminf(min3(c[0], c[1], c[2]), min3(min3(c[3], e[0], e[1]), e[2], e[3]));
+          if (m <= 0.f) {
+            const int word = nb >> 2, sh = (nb & 3) * 8 + 2 * tq;
+            const unsigned m0 = (unsigned)(c[0] <= 0.f) | ((unsigned)(c[1] <= 0.f) << 1);
+            const unsigned m1 = (unsigned)(c[2] <= 0.f) | ((unsigned)(c[3] <= 0.f) << 1);
+            const unsigned m2 = (unsigned)(e[0] <= 0.f) | ((unsigned)(e[1] <= 0.f) << 1);
+            const unsigned m3 = (unsigned)(e[2] <= 0.f) | ((unsigned)(e[3] <= 0.f) << 1);
+            if (m0) atomicOr(&mask[(g) * 4 + word], m0 << sh);
+            if (m1) atomicOr(&mask[(g + 8) * 4 + word], m1 << sh);
+            if (m2) atomicOr(&mask[(g + 16) * 4 + word], m2 << sh);
+            if (m3) atomicOr(&mask[(g + 24) * 4 + word], m3 << sh);
           }
         }
-        bound = fminf(bound, second);
+        __syncwarp();
+        const uint4 mk = *reinterpret_cast<const uint4*>(mask + lane * 4);
+        const bool mine = (mk.x | mk.y | mk.z | mk.w) != 0;
+        if (kFragBufs == 1 && k >= 0) fetch(k, 0);  // (the __syncwarp above: all lanes are done with the buffer)
+        if (!__any_sync(0xffffffffu, mine)) continue;
+        if (mine) {
+          *reinterpret_cast<uint4*>(mask + lane * 4) = make_uint4(0, 0, 0, 0);
+          auto survivors = [&](unsigned bits, int w) {
+            while (bits) {
+              const int bpos = __ffs(bits) - 1;
+              bits &= bits - 1;
+              const long long j = t * kTileRows + w * 32 + bpos;
+              const float* rc = rec + (j >> 1) * kPairFloats + (j & 1);
+              const int oj = __ldg(orig + j);
+              const float d = exact_sqdist10(rc, a);
+              if (d <= bound) update_best_tie(d, oj, best, second, idx);
+            }
+          };
+          survivors(mk.x, 0);
+          survivors(mk.y, 1);
+          survivors(mk.z, 2);
+          survivors(mk.w, 3);
+          bound = fminf(bound, second);
+        }
+        __syncwarp();
+        if (n_warps > 1) {
+          if (second < FLT_MAX) atomicMin(&s_bound[lane], __float_as_int(second));  // second >= 0: int order = float order
+          bound = fminf(bound, __int_as_float(s_bound[lane]));
+        }
+        refresh_thr();
       }
-      __syncwarp();
-      if (n_warps > 1) {
-        if (second < FLT_MAX) atomicMin(&s_bound[lane], __float_as_int(second));  // second >= 0: int order = float order
-        bound = fminf(bound, __int_as_float(s_bound[lane]));
-      }
-      refresh_thr();
     }
   }
   if (n_warps > 1) {
@@ -1139,8 +1232,11 @@ int vo_match_dev(vo_ctx* ctx, const float* d_descA, int64_t n1, const float* d_d
       match_gatherfrag10_kernel<<<(unsigned)((n_tiles * kTileRows + 255) / 256), 256, 0, ctx->stream>>>(
           d_descB, corder, n2, n_tiles * kTileRows, (uint4*)frag);
       VO_CHECK_LAUNCH(ctx, "match_gatherfrag10_kernel");
-      const size_t mma_smem = 1024 + (size_t)n_warps * 512;
-      static_assert(1024 + 512 >= 3 * 32 * 4, "merge arrays reuse the fragment / mask buffers");
+      const size_t mma_smem = 1024 + (size_t)n_warps * kMmaWarpSmem;
+      static_assert(kMmaWarpSmem >= 3 * 32 * 4, "merge arrays reuse the fragment / mask buffers");
+      if (mma_smem > 48 * 1024)
+        VO_CUDA(ctx, cudaFuncSetAttribute(match_scan10_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          1024 + kMaxScanWarps * kMmaWarpSmem));
       match_scan10_mma_kernel<<<(unsigned)groups, 32 * n_warps, mma_smem, ctx->stream>>>(
           d_descA, row_begin, rows, sorted_ids, keys2, rec, orig, frag, box, sbox, ckeys2, n2, range_flag, pb, ps, pi);
       VO_CHECK_LAUNCH(ctx, "match_scan10_mma_kernel");

@@ -4,7 +4,7 @@ R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, R); sys.path.insert(0, os.path.join(R, "tests")); import synth
 vo = importlib.import_module("02-visualodometry_b200")
 ctx = vo.Context(0)
-n1, n2 = 131072, 1 << 20
+n1, n2 = (int(sys.argv[1]) if len(sys.argv) > 1 else 131072), 1 << 20
 A, B = synth.descriptors(n1, n2, seed=42)
 dA, dB = torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda()
 pairs = torch.empty((n1, 2), dtype=torch.int32, device="cuda")
