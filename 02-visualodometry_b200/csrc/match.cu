@@ -552,7 +552,8 @@ __global__ void __launch_bounds__(32 * kMaxScanWarps, VO_SCAN_MINB) match_scan10
 //   k = 0..9 : -2 bf16(a_k)        x  bf16(b_k)
 //   k = 10,11: hi, lo of (1-eps)|a|^2  x  1
 //   k = 12,13: 1                    x  hi, lo of (1-eps)|b|^2
-//   v = (1-eps)(|a|^2+|b|^2) - 2 sum bf16(a_k) bf16(b_k)   (+ accumulation error)
+//   k = 14,15: -hi, -lo of the row's current bound (slightly inflated)  x  1
+//   v = (1-eps)(|a|^2+|b|^2) - 2 sum bf16(a_k) bf16(b_k)   (+ accumulation error);  output = v - bound
 // bf16 rounding: |bf16(x) - x| <= 2^-9 |x|, so 2 |sum a^b^ - sum ab| <= (2^-8 + 2^-18) sum 2|a_k b_k|
 // <= (2^-8 + 2^-18)(|a|^2 + |b|^2); hi/lo split, fp32 norm and accumulator errors are < 2^-15 (|a|^2+|b|^2); the float
 // evaluation of the reference is within 2^-19 of the real distance.  With eps = 2^-8 + 2^-12 that gives
@@ -570,6 +571,14 @@ __device__ __forceinline__ unsigned bf16x2_rn(float lo, float hi) {
   return r;
 }
 
+// (-hi, -lo) of a row's bound as two bf16: hi + lo >= bound (the 2^-14 inflation covers the 2^-17 split error),
+// clamped below bf16's largest finite value so that "no bound yet" stays finite
+__device__ __forceinline__ unsigned filter_bound_word(float bound) {
+  const float t = fminf(bound * 1.00006103515625f, 3.0e38f);
+  const float hi = __uint_as_float(bf16x2_rn(t, 0.f) << 16);
+  return bf16x2_rn(-hi, -(t - hi));
+}
+
 // the 16 bf16 of one point (natural dimension order), as 8 words: w[i] = (k = 2i, 2i+1)
 __device__ __forceinline__ void filter_words(const float v[10], bool is_row, unsigned w[8]) {
   float n = 0.f;
@@ -584,7 +593,7 @@ __device__ __forceinline__ void filter_words(const float v[10], bool is_row, uns
   const unsigned ones = 0x3F803F80u, norm = bf16x2_rn(hi, lo);
   w[5] = is_row ? norm : ones;
   w[6] = is_row ? ones : norm;
-  w[7] = 0u;
+  w[7] = is_row ? filter_bound_word(FLT_MAX) : ones;
 }
 
 __global__ void match_range_check_kernel(const float* __restrict__ x, long long n, int* __restrict__ flag) {
@@ -617,11 +626,10 @@ __global__ void match_gatherfrag10_kernel(const float* __restrict__ B, const uns
   frag[2 * j + 1] = make_uint4(w[2], w[6], w[3], w[7]);
 }
 
-// d = a x b + {c_lo, c_lo, c_hi, c_hi}: the accumulator rows g / g+8 start from one value each
-__device__ __forceinline__ void mma_bf16_16816(float d[4], const unsigned a[4], uint2 b, float c_lo, float c_hi) {
-  asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%11,%11};"
+__device__ __forceinline__ void mma_bf16_16816(float d[4], const unsigned a[4], uint2 b) {
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
       : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b.x), "r"(b.y), "f"(c_lo), "f"(c_hi));
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b.x), "r"(b.y), "f"(0.f));
 }
 __device__ __forceinline__ float min3(float a, float b, float c) {  // FMNMX3; NaN operands are ignored
   float r;
@@ -717,13 +725,16 @@ __global__ void __launch_bounds__(VO_MMA_LB) match_scan10_mma_kernel(
   }
   float best = FLT_MAX, second = FLT_MAX, bound = FLT_MAX;
   int idx = -1;
-  // minus the bounds of rows g, g+8, g+16, g+24 (this thread's outputs): they go into the MMA as the accumulator's
-  // starting value, so a column survives iff its output is <= 0 and eight outputs need one comparison.  (The
-  // bound joins the sum as one more term no larger than the others unless the column is far below it anyway.)
-  float nthr[4] = {-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};
+  // The rows' bounds ride in the A operand (k = 14,15, held by the threads with tq == 3): the MMA output is v - bound,
+  // a column survives iff its output is <= 0, and a running 3-input minimum over 4 column blocks needs one
+  // comparison.  (The bound joins the sum as two more terms; if it dwarfs the others the sign is decided anyway.)
   auto refresh_thr = [&]() {
+    const unsigned tw = filter_bound_word(bound);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) nthr[i] = -__shfl_sync(0xffffffffu, bound, g + 8 * i);
+    for (int i = 0; i < 4; ++i) {
+      const unsigned w = __shfl_sync(0xffffffffu, tw, g + 8 * i);
+      if (tq == 3) afrag[i >> 1][2 + (i & 1)] = w;
+    }
   };
   const long long n_tiles = (n2 + kTileRows - 1) / kTileRows;
   const long long n_super = (n_tiles + kSuper - 1) / kSuper;
@@ -818,22 +829,34 @@ __global__ void __launch_bounds__(VO_MMA_LB) match_scan10_mma_kernel(
         }
         VO_COUNT(1, 1);
 #pragma unroll
-        for (int nb = 0; nb < 16; ++nb) {
-          float c[4], e[4];
-          const uint2 bq = fb[nb * 32];
-          mma_bf16_16816(c, afrag[0], bq, nthr[0], nthr[1]);
-          mma_bf16_16816(e, afrag[1], bq, nthr[2], nthr[3]);
-          const float m = fminf(min3(c[0], c[1], c[2]), min3(min3(c[3], e[0], e[1]), e[2], e[3]));
-          if (m <= 0.f) {
-            const int word = nb >> 2, sh = (nb & 3) * 8 + 2 * tq;
-            const unsigned m0 = (unsigned)(c[0] <= 0.f) | ((unsigned)(c[1] <= 0.f) << 1);
-            const unsigned m1 = (unsigned)(c[2] <= 0.f) | ((unsigned)(c[3] <= 0.f) << 1);
-            const unsigned m2 = (unsigned)(e[0] <= 0.f) | ((unsigned)(e[1] <= 0.f) << 1);
-            const unsigned m3 = (unsigned)(e[2] <= 0.f) | ((unsigned)(e[3] <= 0.f) << 1);
-            if (m0) atomicOr(&mask[(g) * 4 + word], m0 << sh);
-            if (m1) atomicOr(&mask[(g + 8) * 4 + word], m1 << sh);
-            if (m2) atomicOr(&mask[(g + 16) * 4 + word], m2 << sh);
-            if (m3) atomicOr(&mask[(g + 24) * 4 + word], m3 << sh);
+        for (int gq = 0; gq < 4; ++gq) {  // 4 column blocks = 32 columns = one mask word
+          float run = FLT_MAX;
+#pragma unroll
+          for (int nb = 4 * gq; nb < 4 * gq + 4; ++nb) {
+            float c[4], e[4];
+            const uint2 bq = fb[nb * 32];
+            mma_bf16_16816(c, afrag[0], bq);
+            mma_bf16_16816(e, afrag[1], bq);
+            run = min3(min3(c[0], c[1], c[2]), min3(c[3], e[0], e[1]), min3(e[2], e[3], run));
+          }
+          // some column of the 32 survives for some row: redo the blocks and mark (warp-uniform: mma.sync inside)
+          if (__any_sync(0xffffffffu, run <= 0.f)) {
+#pragma unroll 1
+            for (int nb = 4 * gq; nb < 4 * gq + 4; ++nb) {
+              float c[4], e[4];
+              const uint2 bq = fb[nb * 32];
+              mma_bf16_16816(c, afrag[0], bq);
+              mma_bf16_16816(e, afrag[1], bq);
+              const int sh = (nb & 3) * 8 + 2 * tq;
+              const unsigned m0 = (unsigned)(c[0] <= 0.f) | ((unsigned)(c[1] <= 0.f) << 1);
+              const unsigned m1 = (unsigned)(c[2] <= 0.f) | ((unsigned)(c[3] <= 0.f) << 1);
+              const unsigned m2 = (unsigned)(e[0] <= 0.f) | ((unsigned)(e[1] <= 0.f) << 1);
+              const unsigned m3 = (unsigned)(e[2] <= 0.f) | ((unsigned)(e[3] <= 0.f) << 1);
+              if (m0) atomicOr(&mask[(g) * 4 + gq], m0 << sh);
+              if (m1) atomicOr(&mask[(g + 8) * 4 + gq], m1 << sh);
+              if (m2) atomicOr(&mask[(g + 16) * 4 + gq], m2 << sh);
+              if (m3) atomicOr(&mask[(g + 24) * 4 + gq], m3 << sh);
+            }
           }
         }
         __syncwarp();
