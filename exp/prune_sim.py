@@ -24,20 +24,20 @@ def second_best(rows):
         out[i:i + 64] = np.partition(d, 1, axis=1)[:, 1]
     return np.maximum(out, 0)
 
-for dims, bits, boxdims in [((0, 4, 2, 6), 8, None), ((0, 4, 2, 6, 1), 6, None), ((0, 4, 2, 6, 1, 5), 5, None), ((0, 4, 2), 10, None),
-                            ((0, 4, 2, 6), 8, tuple(range(10))), ((0, 4, 2, 6, 1, 5), 5, tuple(range(10)))]:
+GROUP = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+for dims, bits, boxdims in [((0, 4, 2, 6), 8, None)]:
     boxdims = boxdims or dims
     kb = morton(B, list(dims), bits); cb = np.argsort(kb, kind="stable")
     ka = morton(A, list(dims), bits); ra = np.argsort(ka, kind="stable")
     Bs = B[cb][:, boxdims].reshape(-1, 128, len(boxdims))
     blo, bhi = Bs.min(1), Bs.max(1)
-    groups = rng.integers(0, n // 32, 48)
+    groups = rng.integers(0, n // GROUP, 48 * 32 // GROUP)
     fr = []
     for g in groups:
-        rows = ra[g * 32:(g + 1) * 32]
+        rows = ra[g * GROUP:(g + 1) * GROUP]
         sb = second_best(rows)
         p = A[rows][:, boxdims]
         gap = np.maximum(0, np.maximum(blo[None] - p[:, None], p[:, None] - bhi[None]))
         need = ((gap ** 2).sum(2) < sb[:, None]).any(0)
         fr.append(need.mean())
-    print(f"curve dims {dims} x {bits} bits, box dims {len(boxdims)}: tiles needed {100*np.mean(fr):.2f}% (median {100*np.median(fr):.2f}%)", flush=True)
+    print(f"group {GROUP}: curve dims {dims} x {bits} bits, box dims {len(boxdims)}: tiles needed {100*np.mean(fr):.2f}% (median {100*np.median(fr):.2f}%)", flush=True)
