@@ -227,30 +227,42 @@ __device__ __forceinline__ float from_ordered_u32(unsigned u) {
 }
 
 __global__ void match_minmax10_kernel(const float* __restrict__ A, long long row_begin, long long rows,
-                                      unsigned* __restrict__ mm /* [4] min, [4] max, ordered */) {
-  const int dims[4] = {0, 4, 2, 6};
-  unsigned lo[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu}, hi[4] = {0, 0, 0, 0};
+                                      unsigned* __restrict__ mm /* [10] min, [10] max per dimension, ordered */) {
+  unsigned lo[10], hi[10];
+#pragma unroll
+  for (int d = 0; d < 10; ++d) {
+    lo[d] = 0xffffffffu;
+    hi[d] = 0u;
+  }
   for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (long long)gridDim.x * blockDim.x)
 #pragma unroll
-    for (int d = 0; d < 4; ++d) {
-      const float v = __ldg(A + (row_begin + r) * 10 + dims[d]);
-      if (v == v && fabsf(v) <= FLT_MAX) {  // NaN / inf do not stretch the key range
+    for (int d = 0; d < 10; ++d) {
+      const float v = __ldg(A + (row_begin + r) * 10 + d);
+      if (v == v && fabsf(v) <= FLT_MAX) {  // NaN / inf do not stretch the ranges
         const unsigned u = ordered_u32(v);
         lo[d] = min(lo[d], u);
         hi[d] = max(hi[d], u);
       }
     }
 #pragma unroll
-  for (int d = 0; d < 4; ++d) {
+  for (int d = 0; d < 10; ++d) {
     for (int o = 16; o > 0; o >>= 1) {
       lo[d] = min(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], o));
       hi[d] = max(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], o));
     }
     if ((threadIdx.x & 31) == 0) {
       atomicMin(&mm[d], lo[d]);
-      atomicMax(&mm[4 + d], hi[d]);
+      atomicMax(&mm[10 + d], hi[d]);
     }
   }
+}
+
+// midpoint of dimension k's finite range over rows and columns: the filter works on centred descriptors
+// (distances do not change, but its error bound is relative to the squared norms)
+__device__ __forceinline__ float range_center(const unsigned* __restrict__ mm, int k) {
+  const unsigned ul = mm[k], uh = mm[10 + k];
+  if (ul > uh) return 0.f;  // no finite value in this dimension
+  return 0.5f * from_ordered_u32(ul) + 0.5f * from_ordered_u32(uh);
 }
 
 __device__ __forceinline__ unsigned spread8(unsigned v) {  // abcdefgh -> a000b000...h (every 4th bit)
@@ -270,7 +282,7 @@ __global__ void match_keys10_kernel(const float* __restrict__ A, long long row_b
   unsigned key = 0;
 #pragma unroll
   for (int d = 0; d < 4; ++d) {
-    const float lo = from_ordered_u32(mm[d]), hi = from_ordered_u32(mm[4 + d]);
+    const float lo = from_ordered_u32(mm[dims[d]]), hi = from_ordered_u32(mm[10 + dims[d]]);
     const float v = __ldg(A + (row_begin + r) * 10 + dims[d]);
     float q = (hi > lo) ? (v - lo) / (hi - lo) * 255.f : 0.f;
     q = (q == q) ? fminf(fmaxf(q, 0.f), 255.f) : 0.f;
@@ -560,6 +572,8 @@ __global__ void __launch_bounds__(32 * kMaxScanWarps, VO_SCAN_MINB) match_scan10
 //   v < d_reference      for every finite pair whose magnitudes pass match_range_check_kernel (no overflow of the
 //                        norms, no underflow of the products; otherwise the exact scan above runs instead),
 // so v > bound  =>  d > bound >= final second-best: the column cannot change the row's result (strict, ties safe).
+// The filter sees descriptors minus the midpoint c of each dimension's range (same distances; fl(x - c) moves a
+// distance by < 2^-22 of the centred norms), so a common offset of the data does not loosen the bound.
 // Columns with v <= bound are marked in a per-row bit mask and evaluated exactly (reference order, fp32) by the
 // row's lane.  NaN/inf rows or columns give v = NaN/inf: never marked, exactly like `d < best` with a NaN/inf d.
 constexpr float kFilterEps = 0.00390625f + 0.000244140625f;  // 2^-8 + 2^-12
@@ -596,10 +610,11 @@ __device__ __forceinline__ void filter_words(const float v[10], bool is_row, uns
   w[7] = is_row ? filter_bound_word(FLT_MAX) : ones;
 }
 
-__global__ void match_range_check_kernel(const float* __restrict__ x, long long n, int* __restrict__ flag) {
+__global__ void match_range_check_kernel(const float* __restrict__ x, long long n, const unsigned* __restrict__ mm,
+                                         int* __restrict__ flag) {
   bool bad = false;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const float a = fabsf(__ldg(x + i));
+    const float a = fabsf(__ldg(x + i) - range_center(mm, (int)(i % 10)));
     bad |= (a <= FLT_MAX) && ((a > kFilterMaxAbs) || (a != 0.f && a < kFilterMinAbs));
   }
   if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
@@ -608,7 +623,7 @@ __global__ void match_range_check_kernel(const float* __restrict__ x, long long 
 // per column (sorted position j, padded to whole tiles with NaN): uint2[4], entry t = words (t, t+4) = the
 // m16n8k16 B fragment of lane 4*(j%8)+t, so a warp's fragment load for 8 columns is one coalesced 256-byte read
 __global__ void match_gatherfrag10_kernel(const float* __restrict__ B, const unsigned* __restrict__ order, long long n2,
-                                          long long n_padded, uint4* __restrict__ frag) {
+                                          long long n_padded, const unsigned* __restrict__ mm, uint4* __restrict__ frag) {
   const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n_padded) return;
   unsigned w[8];
@@ -616,7 +631,7 @@ __global__ void match_gatherfrag10_kernel(const float* __restrict__ B, const uns
     const long long src = order[j];
     float v[10];
 #pragma unroll
-    for (int k = 0; k < 10; ++k) v[k] = __ldg(B + src * 10 + k);
+    for (int k = 0; k < 10; ++k) v[k] = __ldg(B + src * 10 + k) - range_center(mm, k);
     filter_words(v, false, w);
   } else {
 #pragma unroll
@@ -662,8 +677,9 @@ __global__ void __launch_bounds__(VO_MMA_LB) match_scan10_mma_kernel(
     const float* __restrict__ A, long long row_begin, long long rows, const unsigned* __restrict__ row_order,
     const unsigned* __restrict__ row_keys_sorted, const float* __restrict__ rec, const int* __restrict__ orig,
     const uint2* __restrict__ frag, const float* __restrict__ box, const float* __restrict__ sbox,
-    const unsigned* __restrict__ col_keys_sorted, long long n2, const int* __restrict__ range_flag,
-    float* __restrict__ o_best, float* __restrict__ o_second, int* __restrict__ o_idx) {
+    const unsigned* __restrict__ col_keys_sorted, long long n2, const unsigned* __restrict__ mm,
+    const int* __restrict__ range_flag, float* __restrict__ o_best, float* __restrict__ o_second,
+    int* __restrict__ o_idx) {
   if (*range_flag != 0) return;  // magnitudes outside the filter's error analysis: the exact scan runs instead
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ long long s_t0;
@@ -696,6 +712,8 @@ __global__ void __launch_bounds__(VO_MMA_LB) match_scan10_mma_kernel(
     }
     if (warp == 0) {
       unsigned w[8];
+#pragma unroll
+      for (int k = 0; k < 10; ++k) v[k] -= range_center(mm, k);
       filter_words(v, true, w);
 #pragma unroll
       for (int i = 0; i < 8; ++i) sA[lane * 8 + i] = w[i];
@@ -1174,7 +1192,7 @@ int vo_match_dev(vo_ctx* ctx, const float* d_descA, int64_t n1, const float* d_d
   const long long n2p = (n2 + 1) & ~1ll, n_tiles = (n2 + kTileRows - 1) / kTileRows;
   const size_t o_keys = carve(ordered ? (size_t)rows * 4 : 0), o_keys2 = carve(ordered ? (size_t)rows * 4 : 0);
   const size_t o_ids = carve(ordered ? (size_t)rows * 4 : 0), o_order = carve(ordered ? (size_t)rows * 4 : 0);
-  const size_t o_mm = carve(64), o_sorttmp = carve(sort_tmp_bytes);
+  const size_t o_mm = carve(128), o_sorttmp = carve(sort_tmp_bytes);
   const size_t o_ckeys = carve(indexed ? (size_t)n2 * 4 : 0), o_ckeys2 = carve(indexed ? (size_t)n2 * 4 : 0);
   const size_t o_cids = carve(indexed ? (size_t)n2 * 4 : 0), o_corder = carve(indexed ? (size_t)n2 * 4 : 0);
   const size_t o_rec = carve(indexed ? (size_t)n2p * 10 * 4 : 0), o_orig = carve(indexed ? (size_t)n2p * 4 : 0);
@@ -1204,8 +1222,8 @@ int vo_match_dev(vo_ctx* ctx, const float* d_descA, int64_t n1, const float* d_d
     unsigned* ids = (unsigned*)(base + o_ids);
     unsigned* sorted_ids = (unsigned*)(base + o_order);
     unsigned* mm = (unsigned*)(base + o_mm);
-    VO_CUDA(ctx, cudaMemsetAsync(mm, 0xFF, 16, ctx->stream));
-    VO_CUDA(ctx, cudaMemsetAsync(mm + 4, 0x00, 16, ctx->stream));
+    VO_CUDA(ctx, cudaMemsetAsync(mm, 0xFF, 40, ctx->stream));
+    VO_CUDA(ctx, cudaMemsetAsync(mm + 10, 0x00, 40, ctx->stream));
     match_minmax10_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(d_descA, row_begin, rows, mm);
     VO_CHECK_LAUNCH(ctx, "match_minmax10_kernel");
     if (indexed) {  // one key range for rows and columns
@@ -1244,13 +1262,13 @@ int vo_match_dev(vo_ctx* ctx, const float* d_descA, int64_t n1, const float* d_d
       while (n_warps < kMaxScanWarps && groups * n_warps * 2 <= (long long)ctx->sm_count * 32) n_warps *= 2;
       // magnitudes the filter's error analysis does not cover select the exact scan (flag read on the device)
       int* range_flag = (int*)(base + o_small + 32);
-      match_range_check_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(d_descA + row_begin * 10, rows * 10, range_flag);
+      match_range_check_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(d_descA + row_begin * 10, rows * 10, mm, range_flag);
       VO_CHECK_LAUNCH(ctx, "match_range_check_kernel");
-      match_range_check_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(d_descB, n2 * 10, range_flag);
+      match_range_check_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(d_descB, n2 * 10, mm, range_flag);
       VO_CHECK_LAUNCH(ctx, "match_range_check_kernel");
       uint2* frag = (uint2*)(base + o_frag);
       match_gatherfrag10_kernel<<<(unsigned)((n_tiles * kTileRows + 255) / 256), 256, 0, ctx->stream>>>(
-          d_descB, corder, n2, n_tiles * kTileRows, (uint4*)frag);
+          d_descB, corder, n2, n_tiles * kTileRows, mm, (uint4*)frag);
       VO_CHECK_LAUNCH(ctx, "match_gatherfrag10_kernel");
       const size_t mma_smem = 1024 + (size_t)n_warps * kMmaWarpSmem;
       static_assert(kMmaWarpSmem >= 3 * 32 * 4, "merge arrays reuse the fragment / mask buffers");
@@ -1258,7 +1276,7 @@ int vo_match_dev(vo_ctx* ctx, const float* d_descA, int64_t n1, const float* d_d
         VO_CUDA(ctx, cudaFuncSetAttribute(match_scan10_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           1024 + kMaxScanWarps * kMmaWarpSmem));
       match_scan10_mma_kernel<<<(unsigned)groups, 32 * n_warps, mma_smem, ctx->stream>>>(
-          d_descA, row_begin, rows, sorted_ids, keys2, rec, orig, frag, box, sbox, ckeys2, n2, range_flag, pb, ps, pi);
+          d_descA, row_begin, rows, sorted_ids, keys2, rec, orig, frag, box, sbox, ckeys2, n2, mm, range_flag, pb, ps, pi);
       VO_CHECK_LAUNCH(ctx, "match_scan10_mma_kernel");
       const size_t scan_smem = (size_t)n_warps * kTileBytes;
       static_assert(kTileBytes >= 3 * 32 * 4, "merge arrays reuse the tile buffers");

@@ -80,6 +80,20 @@ def test_match_indexed_path_bit_exact(ctx, oracle, n1, n2, noise, dup, scale):
     assert np.array_equal(ps, rp[(rp[:, 0] >= lo) & (rp[:, 0] < hi)])
 
 
+def test_match_indexed_path_offset_descriptors(ctx, oracle):
+    """descriptors with a large common offset (|x| ~ 100, spread ~ 1): the filter centres them, the exact evaluation
+    does not - results are those of the reference on the data as given"""
+    A, B = synth.descriptors(9000, 10000, seed=3, copy_frac=0.8, dup_frac=0.01, noise=0.03)
+    off = np.linspace(-120, 150, 10).astype(np.float32)
+    A, B = (A + off).astype(np.float32), (B + off).astype(np.float32)
+    rp, _, rbest, rsecond, ridx = oracle.match(A, B, want_rows=True, n_threads=8)
+    p2, best, second, idx = _rows_dev(ctx, A, B)
+    assert np.array_equal(idx, ridx)
+    assert np.array_equal(best.view(np.uint32), rbest.view(np.uint32))
+    assert np.array_equal(second.view(np.uint32), rsecond.view(np.uint32))
+    assert np.array_equal(p2, rp)
+
+
 def test_match_indexed_path_nonfinite(ctx, oracle):
     """NaN / inf descriptors inside the indexed path: a NaN or inf distance never wins (`d < best` is false),
     on the filter exactly as in the reference loop"""
