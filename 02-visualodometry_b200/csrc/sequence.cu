@@ -86,7 +86,10 @@ __device__ __forceinline__ bool accept_match(int idx, float best, float second, 
   return (idx != -1) && (best < dist_thr) && (__fdiv_rn(best, second) < ratio_thr);
 }
 
-__global__ void __launch_bounds__(kSeqThreads, 4) seq_pipeline_kernel(const SeqArgs a) {
+#ifndef VO_SEQ_MINB
+#define VO_SEQ_MINB 6
+#endif
+__global__ void __launch_bounds__(kSeqThreads, VO_SEQ_MINB) seq_pipeline_kernel(const SeqArgs a) {
   __shared__ FrameBuf s_curr, s_next;
   __shared__ __align__(16) float s_tile[kSeqThreads * kDimPad];  // map descriptors, 128 rows at a time
   __shared__ int2 s_iw[kSeqThreads];                              // (image idx in next, world idx)
@@ -94,6 +97,7 @@ __global__ void __launch_bounds__(kSeqThreads, 4) seq_pipeline_kernel(const SeqA
   __shared__ unsigned char s_matched[kSeqThreads];                // next-frame point already in the map
   __shared__ int s_warp[kSeqWarps];
   __shared__ float s_red[kSeqWarps][32];
+  __shared__ double s_sum[32];
   __shared__ double s_mom[kSeqWarps][kMom];
   __shared__ float s_pose[12];   // world-in-camera during PICP
   __shared__ float s_prev[12];   // camera-in-world of the previous frame
@@ -306,24 +310,27 @@ __global__ void __launch_bounds__(kSeqThreads, 4) seq_pipeline_kernel(const SeqA
         s_red[warp][30] = __int_as_float(n_out);
       }
       __syncthreads();
+      // cross-warp sums: thread k adds the warps' partials of term k in warp order, in double (one thread doing all
+      // 29 of them was 40 % of the round: 350 dependent instructions while 127 threads wait at the barrier)
+      if (tid < 29) {
+        double v = 0;
+#pragma unroll
+        for (int w = 0; w < kSeqWarps; ++w) v += (double)s_red[w][tid];
+        s_sum[tid] = v;
+      } else if (tid == 29) {
+        int inl = 0;
+#pragma unroll
+        for (int w = 0; w < kSeqWarps; ++w) inl += __float_as_int(s_red[w][29]);
+        s_warp[0] = inl;
+      }
+      __syncthreads();
       if (tid == 0) {
         float Hu[21], bb[6];
-        double chi_in = 0;
-        int inl = 0;
-        for (int k = 0; k < 21; ++k) {
-          double v = 0;
-          for (int w = 0; w < kSeqWarps; ++w) v += (double)s_red[w][k];
-          Hu[k] = (float)v;
-        }
-        for (int k = 0; k < 6; ++k) {
-          double v = 0;
-          for (int w = 0; w < kSeqWarps; ++w) v += (double)s_red[w][21 + k];
-          bb[k] = (float)v;
-        }
-        for (int w = 0; w < kSeqWarps; ++w) {
-          chi_in += (double)s_red[w][27];
-          inl += __float_as_int(s_red[w][29]);
-        }
+#pragma unroll
+        for (int k = 0; k < 21; ++k) Hu[k] = (float)s_sum[k];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) bb[k] = (float)s_sum[21 + k];
+        const double chi_in = s_sum[27];
         float pose[12];
         for (int i = 0; i < 12; ++i) pose[i] = s_pose[i];
         picp_gn_step(Hu, bb, a.p.damping, pose);
@@ -332,7 +339,6 @@ __global__ void __launch_bounds__(kSeqThreads, 4) seq_pipeline_kernel(const SeqA
         const float rel = (prev > 1e-10f) ? __fdiv_rn(fabsf(__fsub_rn(prev, cur)), prev) : 0.f;
         s_prev_chi = cur;
         s_flag = (rel < a.p.rel_tol) ? 1 : 0;  // icp_test.cpp:99-106
-        s_warp[0] = inl;
       }
       __syncthreads();
       rounds_done = r + 1;
