@@ -96,8 +96,9 @@ __global__ void __launch_bounds__(kSeqThreads, VO_SEQ_MINB) seq_pipeline_kernel(
   __shared__ int2 s_im[kSeqThreads];                              // (idx in curr, idx in next)
   __shared__ unsigned char s_matched[kSeqThreads];                // next-frame point already in the map
   __shared__ int s_warp[kSeqWarps];
-  __shared__ float s_red[kSeqWarps][32];
-  __shared__ double s_sum[32];
+  __shared__ float s_red[2][kSeqWarps][32];
+  __shared__ int2 s_verdict[2];
+  __shared__ float s_dx[6];
   __shared__ double s_mom[kSeqWarps][kMom];
   __shared__ float s_pose[12];   // world-in-camera during PICP
   __shared__ float s_prev[12];   // camera-in-world of the previous frame
@@ -302,49 +303,51 @@ __global__ void __launch_bounds__(kSeqThreads, VO_SEQ_MINB) seq_pipeline_kernel(
       for (int i = 0; i < 29; ++i) acc[i] = warp_sum(acc[i]);
       n_in = warp_sum_i(n_in);
       n_out = warp_sum_i(n_out);
-      __syncthreads();
+      // Two barriers per round.  The per-warp partials and the round's verdict are double-buffered by round parity,
+      // so a warp that runs ahead into the next round never overwrites what a slower warp still has to read.
+      const int par = r & 1;
       if (lane == 0) {
 #pragma unroll
-        for (int i = 0; i < 29; ++i) s_red[warp][i] = acc[i];
-        s_red[warp][29] = __int_as_float(n_in);
-        s_red[warp][30] = __int_as_float(n_out);
+        for (int i = 0; i < 29; ++i) s_red[par][warp][i] = acc[i];
+        s_red[par][warp][29] = __int_as_float(n_in);
+        s_red[par][warp][30] = __int_as_float(n_out);
       }
       __syncthreads();
-      // cross-warp sums: thread k adds the warps' partials of term k in warp order, in double (one thread doing all
-      // 29 of them was 40 % of the round: 350 dependent instructions while 127 threads wait at the barrier)
-      if (tid < 29) {
+      if (warp == 0) {
+        // lane k adds the warps' partials of term k in warp order, in double; lane 0 collects them by shuffle,
+        // solves the 6x6 system, and the warp applies the increment (12 pose entries in parallel)
         double v = 0;
-#pragma unroll
-        for (int w = 0; w < kSeqWarps; ++w) v += (double)s_red[w][tid];
-        s_sum[tid] = v;
-      } else if (tid == 29) {
         int inl = 0;
 #pragma unroll
-        for (int w = 0; w < kSeqWarps; ++w) inl += __float_as_int(s_red[w][29]);
-        s_warp[0] = inl;
-      }
-      __syncthreads();
-      if (tid == 0) {
+        for (int w = 0; w < kSeqWarps; ++w) {
+          v += (double)s_red[par][w][lane];
+          inl += __float_as_int(s_red[par][w][29]);
+        }
+        const float vf = (float)v;
         float Hu[21], bb[6];
 #pragma unroll
-        for (int k = 0; k < 21; ++k) Hu[k] = (float)s_sum[k];
+        for (int k = 0; k < 21; ++k) Hu[k] = __shfl_sync(0xffffffffu, vf, k);
 #pragma unroll
-        for (int k = 0; k < 6; ++k) bb[k] = (float)s_sum[21 + k];
-        const double chi_in = s_sum[27];
-        float pose[12];
-        for (int i = 0; i < 12; ++i) pose[i] = s_pose[i];
-        picp_gn_step(Hu, bb, a.p.damping, pose);
-        for (int i = 0; i < 12; ++i) s_pose[i] = pose[i];
-        const float cur = (float)chi_in, prev = s_prev_chi;
-        const float rel = (prev > 1e-10f) ? __fdiv_rn(fabsf(__fsub_rn(prev, cur)), prev) : 0.f;
-        s_prev_chi = cur;
-        s_flag = (rel < a.p.rel_tol) ? 1 : 0;  // icp_test.cpp:99-106
+        for (int k = 0; k < 6; ++k) bb[k] = __shfl_sync(0xffffffffu, vf, 21 + k);
+        const float cur = __shfl_sync(0xffffffffu, vf, 27);
+        if (tid == 0) {
+          float dx[6];
+          picp_gn_solve(Hu, bb, a.p.damping, dx);
+#pragma unroll
+          for (int k = 0; k < 6; ++k) s_dx[k] = dx[k];
+          const float prev = s_prev_chi;
+          const float rel = (prev > 1e-10f) ? __fdiv_rn(fabsf(__fsub_rn(prev, cur)), prev) : 0.f;
+          s_prev_chi = cur;
+          s_verdict[par] = make_int2((rel < a.p.rel_tol) ? 1 : 0, inl);  // icp_test.cpp:99-106
+        }
+        __syncwarp();
+        picp_apply_dx_warp(s_dx, s_pose, lane);
       }
       __syncthreads();
       rounds_done = r + 1;
-      last_inl = s_warp[0];
-      const bool stop = s_flag != 0;
-      __syncthreads();
+      const int2 verdict = s_verdict[par];
+      last_inl = verdict.y;
+      const bool stop = verdict.x != 0;
       if (stop) break;
     }
     // (3) estimated camera-in-world pose of the next frame
