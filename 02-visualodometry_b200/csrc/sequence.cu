@@ -265,9 +265,9 @@ __global__ void __launch_bounds__(kSeqThreads, VO_SEQ_MINB) seq_pipeline_kernel(
       float T[12];
 #pragma unroll
       for (int i = 0; i < 12; ++i) T[i] = s_pose[i];
-      float acc[29];
+      float acc[32];  // 21 H + 6 b + chi_in + chi_out + n_in + n_out (small counts are exact in float) + pad
 #pragma unroll
-      for (int i = 0; i < 29; ++i) acc[i] = 0.f;
+      for (int i = 0; i < 32; ++i) acc[i] = 0.f;
       int n_in = 0, n_out = 0;
       if (tid < C) {
         const PointTerms t = pinhole ? picp_project<true>(cam, T, a.p.kernel_threshold, wx, wy, wz, zu, zv, true)
@@ -299,19 +299,13 @@ __global__ void __launch_bounds__(kSeqThreads, VO_SEQ_MINB) seq_pipeline_kernel(
           }
         }
       }
-#pragma unroll
-      for (int i = 0; i < 29; ++i) acc[i] = warp_sum(acc[i]);
-      n_in = warp_sum_i(n_in);
-      n_out = warp_sum_i(n_out);
+      acc[29] = (float)n_in;
+      acc[30] = (float)n_out;
+      const float mine = warp_sum32_scatter(acc, lane);  // lane k: this warp's total of term k
       // Two barriers per round.  The per-warp partials and the round's verdict are double-buffered by round parity,
       // so a warp that runs ahead into the next round never overwrites what a slower warp still has to read.
       const int par = r & 1;
-      if (lane == 0) {
-#pragma unroll
-        for (int i = 0; i < 29; ++i) s_red[par][warp][i] = acc[i];
-        s_red[par][warp][29] = __int_as_float(n_in);
-        s_red[par][warp][30] = __int_as_float(n_out);
-      }
+      s_red[par][warp][lane] = mine;
       __syncthreads();
       if (warp == 0) {
         // lane k adds the warps' partials of term k in warp order, in double; lane 0 collects them by shuffle,
@@ -321,7 +315,7 @@ __global__ void __launch_bounds__(kSeqThreads, VO_SEQ_MINB) seq_pipeline_kernel(
 #pragma unroll
         for (int w = 0; w < kSeqWarps; ++w) {
           v += (double)s_red[par][w][lane];
-          inl += __float_as_int(s_red[par][w][29]);
+          inl += (int)s_red[par][w][29];
         }
         const float vf = (float)v;
         float Hu[21], bb[6];

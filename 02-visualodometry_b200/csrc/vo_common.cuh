@@ -89,6 +89,22 @@ __device__ __forceinline__ float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+// 32 values per lane -> lane L returns the warp total of value L.  Recursive halving: 31 shuffles instead of
+// 32 x 5; every total is built over the same butterfly tree (partners L^16, L^8, ..., L^1) as warp_sum, so the
+// two give bit-identical sums.
+__device__ __forceinline__ float warp_sum32_scatter(float (&v)[32], int lane) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const bool upper = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < o; ++i) {
+      const float send = upper ? v[i] : v[i + o];
+      const float keep = upper ? v[i + o] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  return v[0];
+}
 __device__ __forceinline__ int warp_sum_i(int v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
