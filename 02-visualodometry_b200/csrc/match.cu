@@ -94,48 +94,7 @@ __global__ void __launch_bounds__(kMatchThreads) match_scan_kernel(
 // never exceeds the full distance d.  A column can only change (best, second, idx) when d < second,
 // hence when lb < second; if no lane of the warp has such a column the other 6 dimensions and the
 // update are skipped.  Results are bit-identical to the unpruned scan.
-typedef unsigned long long f2;
-__device__ __forceinline__ f2 pack2(float lo, float hi) {
-  f2 r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ void unpack2(f2 v, float& lo, float& hi) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ f2 add2(f2 a, f2 b) {
-  f2 d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-__device__ __forceinline__ f2 sub2(f2 a, f2 b) {
-  f2 d;
-  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
-  f2 d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-// (a-b)^2 with ONE rounding of the product. ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even
-// under --fmad=false (observed with CUDA 12.9), which would change the last bit of the distance; an
-// explicit fma with a +0 addend rounds exactly like the multiplication and cannot be fused again.
-__device__ __forceinline__ f2 sq2(f2 a, f2 b) {
-  const f2 d = sub2(a, b);
-  return fma2(d, d, 0ull);
-}
-
-constexpr int kPairFloats = 20;  // one column pair in shared memory
-__device__ __forceinline__ int dim_slot10(int k) {  // position of dimension k inside a pair record
-  const int order[10] = {0, 4, 1, 5, 2, 6, 3, 7, 8, 9};  // slot of dim k: dims stored as 0,4,2,6,1,5,3,7,8,9
-  // dims 0,4,2,6,1,5,3,7,8,9 occupy slots 0..9 -> inverse permutation
-  (void)order;
-  switch (k) {
-    case 0: return 0; case 4: return 1; case 2: return 2; case 6: return 3; case 1: return 4;
-    case 5: return 5; case 3: return 6; case 7: return 7; case 8: return 8; default: return 9;
-  }
-}
+// (f2 / pack2 / add2 / sq2 / dim_slot10 / kPairFloats: vo_device.cuh, shared with the sequence kernel)
 
 __global__ void __launch_bounds__(kMatchThreads) match_scan10_kernel(
     const float* __restrict__ A, long long row_begin, long long row_end, const float* __restrict__ B,

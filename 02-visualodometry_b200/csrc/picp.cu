@@ -93,36 +93,13 @@ struct LinArgs {
 // ---- packed f32x2 arithmetic (sm_100a): one instruction, two IEEE round-to-nearest float ops.
 // The FP32 pipe retires the same lanes per clock either way; packing halves the issue slots, which
 // is what bounds this kernel (profiles/r01_picp_linearize_v1.md).
-typedef unsigned long long f2;
-__device__ __forceinline__ f2 pack2(float lo, float hi) {
-  f2 r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ void unpack2(f2 v, float& lo, float& hi) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
-  f2 d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
+// (f2, pack2, unpack2, add2, sub2, fma2: vo_device.cuh)
 __device__ __forceinline__ f2 mul2(f2 a, f2 b) {
   f2 d;
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
 }
 __device__ __forceinline__ f2 neg2(f2 a) { return a ^ 0x8000000080000000ull; }
-__device__ __forceinline__ f2 add2(f2 a, f2 b) {
-  f2 d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-__device__ __forceinline__ f2 sub2(f2 a, f2 b) {
-  f2 d;
-  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
 // a*b rounded once and never contracted into a following add (see the note in picp_pair)
 __device__ __forceinline__ f2 prod2(f2 a, f2 b) { return fma2(a, b, 0ull); }
 

@@ -86,6 +86,8 @@ __device__ __forceinline__ bool accept_match(int idx, float best, float second, 
   return (idx != -1) && (best < dist_thr) && (__fdiv_rn(best, second) < ratio_thr);
 }
 
+__constant__ float kIdentity12[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+
 #ifndef VO_SEQ_MINB
 #define VO_SEQ_MINB 6
 #endif
@@ -117,7 +119,9 @@ __global__ void __launch_bounds__(kSeqThreads, VO_SEQ_MINB) seq_pipeline_kernel(
   float* const w_desc = a.w_desc + seq * (long long)a.world_cap * kDim;
   int* const w_id = a.w_id + seq * (long long)a.world_cap;
   float* const poses = a.poses + seq * (long long)a.n_frames * 12;
-  const float I12[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+  // (constant memory, not a per-thread array: a dynamically indexed local copy was found clobbered by the
+  // cheirality stage's stack temporaries in one build - see profiles/r01_sequences.md)
+  const float* const I12 = kIdentity12;
 
   if (tid < 12)
     for (int f = 0; f < a.n_frames; ++f) poses[f * 12 + tid] = I12[tid];
