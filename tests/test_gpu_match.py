@@ -80,6 +80,18 @@ def test_match_indexed_path_bit_exact(ctx, oracle, n1, n2, noise, dup, scale):
     assert np.array_equal(ps, rp[(rp[:, 0] >= lo) & (rp[:, 0] < hi)])
 
 
+def test_match_few_rows_many_columns_takes_the_indexed_path(ctx, oracle):
+    """300 query rows against 1,000,000 columns (a frame against a very large map): 10 row groups x 16 warps walk
+    the column index; values, indices and pairs are still the reference's"""
+    A, B = synth.descriptors(300, 1_000_000, seed=11, copy_frac=0.8, dup_frac=0.001, noise=0.02)
+    rp, _, rbest, rsecond, ridx = oracle.match(A, B, want_rows=True, n_threads=8)
+    p2, best, second, idx = _rows_dev(ctx, A, B)
+    assert np.array_equal(idx, ridx)
+    assert np.array_equal(best.view(np.uint32), rbest.view(np.uint32))
+    assert np.array_equal(second.view(np.uint32), rsecond.view(np.uint32))
+    assert np.array_equal(p2, rp)
+
+
 def test_match_indexed_path_offset_descriptors(ctx, oracle):
     """descriptors with a large common offset (|x| ~ 100, spread ~ 1): the filter centres them, the exact evaluation
     does not - results are those of the reference on the data as given"""
