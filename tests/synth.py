@@ -80,3 +80,43 @@ def descriptors(n1, n2, dim=10, seed=42, copy_frac=0.9, dup_frac=0.001, noise=0.
     if noise > 0:
         A = (A + rng.normal(0, noise, A.shape)).astype(np.float32)
     return np.ascontiguousarray(A), np.ascontiguousarray(B)
+
+
+def stress_descriptors(rng, kind, n1, n2):
+    """Adversarial descriptor sets for the matcher (exp/match_stress.py, tests/test_gpu_match.py): clustered, lattice
+    (masses of exact ties and zero distances), low-rank, heavy-tailed; 60 % of the rows are (noisy) copies of
+    columns; a random common scale (1e-3 .. 1e8) and a random common offset (up to 100x the spread)."""
+    if kind == "uniform":
+        B = rng.uniform(-1, 1, (n2, 10)); A = rng.uniform(-1, 1, (n1, 10))
+    elif kind == "clustered":
+        c = rng.uniform(-1, 1, (rng.integers(3, 40), 10))
+        B = c[rng.integers(0, len(c), n2)] + rng.normal(0, 0.02, (n2, 10))
+        A = c[rng.integers(0, len(c), n1)] + rng.normal(0, 0.02, (n1, 10))
+    elif kind == "lattice":
+        B = rng.integers(-2, 3, (n2, 10)) * 0.25; A = rng.integers(-2, 3, (n1, 10)) * 0.25
+    elif kind == "lowrank":
+        M = rng.normal(0, 1, (3, 10))
+        B = rng.normal(0, 1, (n2, 3)) @ M; A = rng.normal(0, 1, (n1, 3)) @ M
+    else:  # "cauchy"
+        B = rng.standard_cauchy((n2, 10)); A = rng.standard_cauchy((n1, 10))
+    A = A.astype(np.float32); B = B.astype(np.float32)
+    cp = rng.random(n1) < 0.6
+    A[cp] = B[rng.integers(0, n2, int(cp.sum()))] + rng.normal(0, rng.choice([0.0, 0.01, 0.1]), (int(cp.sum()), 10)).astype(np.float32)
+    s = np.float32(rng.choice([1.0, 1.0, 1e-3, 250.0, 1e8]))
+    off = (rng.uniform(-5, 5, 10) * rng.choice([0.0, 1.0, 100.0])).astype(np.float32)
+    return np.ascontiguousarray(A * s + off * s), np.ascontiguousarray(B * s + off * s)
+
+
+def stress_case(rng):
+    """one random (kind, A, B, dist_thr, ratio_thr) sized to land on the matcher's indexed path"""
+    kind = str(rng.choice(["uniform", "clustered", "lattice", "lowrank", "cauchy"]))
+    n1 = int(rng.choice([33, 300, 4097, 9000, 20000])); n2 = int(rng.integers(8192, 40000))
+    if n1 < 8192 and n1 * n2 < (1 << 28):
+        n2 = max(n2, (1 << 28) // n1 + 1)
+    n2 = min(n2, 1_200_000)
+    A, B = stress_descriptors(rng, kind, n1, n2)
+    if rng.random() < 0.5:
+        thr = (0.2, 0.8)
+    else:
+        thr = (float(np.float32(np.median(np.abs(A)) ** 2 * 4 + 1e-30)), 1.5)
+    return kind, A, B, thr[0], thr[1]

@@ -80,6 +80,31 @@ def test_match_indexed_path_bit_exact(ctx, oracle, n1, n2, noise, dup, scale):
     assert np.array_equal(ps, rp[(rp[:, 0] >= lo) & (rp[:, 0] < hi)])
 
 
+@pytest.mark.parametrize("seed", [1, 2])
+def test_match_indexed_path_adversarial_sweep(ctx, oracle, seed):
+    """random sizes x {uniform, clustered, lattice, low-rank, heavy-tailed} x common scale 1e-3..1e8 x common offset
+    up to 100x the spread x two threshold pairs: the cases where a lower-bound filter is most likely to be wrong
+    (near-duplicates with aligned rounding errors, norms far above the distances, huge dynamic range). Seed 1 is the
+    sweep that caught the filter's first, too small, error constant."""
+    rng = np.random.default_rng(seed)
+    for case in range(10):
+        kind, A, B, dist_thr, ratio_thr = synth.stress_case(rng)
+        rp, _, rbest, rsecond, ridx = oracle.match(A, B, dist_thr=dist_thr, ratio_thr=ratio_thr, want_rows=True, n_threads=16)
+        import torch
+        n1 = len(A)
+        dA, dB = torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda()
+        best = torch.empty(n1, dtype=torch.float32, device="cuda"); second = torch.empty_like(best)
+        idx = torch.empty(n1, dtype=torch.int32, device="cuda"); pairs = torch.empty((n1, 2), dtype=torch.int32, device="cuda")
+        n, _ = ctx.match_dev(dA.data_ptr(), n1, dB.data_ptr(), len(B), 10, pairs.data_ptr(), n1, dist_thr=dist_thr,
+                             ratio_thr=ratio_thr, d_best=best.data_ptr(), d_second=second.data_ptr(), d_idx=idx.data_ptr())
+        torch.cuda.synchronize()
+        tag = f"seed {seed} case {case} {kind} {n1} x {len(B)}"
+        assert np.array_equal(idx.cpu().numpy(), ridx), tag
+        assert np.array_equal(best.cpu().numpy().view(np.uint32), rbest.view(np.uint32)), tag
+        assert np.array_equal(second.cpu().numpy().view(np.uint32), rsecond.view(np.uint32)), tag
+        assert np.array_equal(pairs[:n].cpu().numpy(), rp), tag
+
+
 def test_match_few_rows_many_columns_takes_the_indexed_path(ctx, oracle):
     """300 query rows against 1,000,000 columns (a frame against a very large map): 10 row groups x 16 warps walk
     the column index; values, indices and pairs are still the reference's"""
