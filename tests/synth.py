@@ -120,3 +120,42 @@ def stress_case(rng):
     else:
         thr = (float(np.float32(np.median(np.abs(A)) ** 2 * 4 + 1e-30)), 1.5)
     return kind, A, B, thr[0], thr[1]
+
+
+def picp_stress_case(rng):
+    """Adversarial PICP frame (exp/picp_stress.py, tests/test_gpu_picp.py): random camera (pinhole or general K), any
+    rotation, scene scale 1e-3..1e6, points in front of / behind / on the camera plane, border-pixel measurements,
+    optional NaN / inf / overflowing points, random thresholds.  Returns
+    (K, rows, cols, pose, world, image, pairs, thr, keep_outliers, general, scale)."""
+    n = int(rng.choice([1, 3, 5, 1000, 1408, 1409, 50001, 300000]))
+    scale = float(rng.choice([1e-3, 1.0, 1.0, 40.0, 1e6]))
+    general = rng.random() < 0.4
+    K = np.array([[rng.uniform(50, 900), 0, rng.uniform(100, 700)], [0, rng.uniform(50, 900), rng.uniform(100, 500)], [0, 0, 1]], np.float32)
+    if general:
+        K[0, 1] = rng.normal(0, 2); K[1, 0] = rng.normal(0, 0.5); K[2, 0] = rng.normal(0, 1e-4); K[2, 1] = rng.normal(0, 1e-4); K[2, 2] = rng.uniform(0.5, 2)
+    rows, cols = int(rng.integers(100, 1000)), int(rng.integers(100, 1300))
+    ang = rng.uniform(-3.1, 3.1, 3) * rng.choice([0.02, 1.0])
+    pose = euler_pose(np.array([*(rng.normal(0, 1, 3) * scale), *ang])).astype(np.float32)
+    # points: in front / behind / at z ~ 0 / far away / NaN / inf
+    cam = np.stack([rng.normal(0, 1, n), rng.normal(0, 1, n), rng.uniform(-1, 6, n)], 1) * scale
+    knd = rng.random(n)
+    cam[knd < 0.03, 2] = rng.normal(0, 1e-6, int((knd < 0.03).sum())) * scale      # z ~ 0 both signs
+    inject = rng.random() < 0.4   # non-finite / overflowing points make the reference's H non-finite too
+    if inject:
+        cam[(knd > 0.03) & (knd < 0.05)] *= 1e12                                       # overflow territory
+    world = ((cam - pose[:, 3].astype(np.float64)) @ pose[:, :3].astype(np.float64)).astype(np.float32)
+    if inject:
+        world[(knd > 0.05) & (knd < 0.055)] = np.nan
+        world[(knd > 0.055) & (knd < 0.06), int(rng.integers(0, 3))] = np.inf
+    Kd = K.astype(np.float64)
+    q = cam @ Kd.T
+    with np.errstate(all="ignore"):
+        uv = q[:, :2] / q[:, 2:3]
+    image = (uv + rng.normal(0, rng.choice([0.0, 0.5, 30.0]), (n, 2))).astype(np.float32)
+    image[~np.isfinite(image)] = 0
+    edge = rng.random(n) < 0.05   # measurements exactly on the border pixels
+    image[edge] = np.stack([rng.choice([0.0, cols - 1.0], int(edge.sum())), rng.choice([0.0, rows - 1.0], int(edge.sum()))], 1)
+    pairs = np.stack([rng.integers(0, n, n), rng.integers(0, n, n)], 1).astype(np.int32)
+    thr = float(rng.choice([1.0, 1000.0, 3000.0, 1e-6, 1e12]))
+    keep = bool(rng.random() < 0.5)
+    return K, rows, cols, pose, world, image, pairs, thr, keep, general, scale

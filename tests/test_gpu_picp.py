@@ -95,6 +95,33 @@ def test_linearize_edge_values(ctx, oracle):
             s.close()
 
 
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_linearize_adversarial_sweep(ctx, oracle, seed):
+    """random cameras (pinhole / general K), any rotation, scene scales 1e-3..1e6, points behind and on the camera
+    plane, border-pixel measurements, NaN / inf / overflowing points, thresholds 1e-6..1e12 (exp/picp_stress.py):
+    the per-correspondence status is bit-exact, H and b within 1e-4 whenever the reference's are finite"""
+    rng = np.random.default_rng(seed)
+    for case in range(12):
+        K, rows, cols, pose, world, image, pairs, thr, keep, general, scale = synth.picp_stress_case(rng)
+        s = ctx.picp()
+        s.set_camera(K, rows, cols, pose)
+        s.set_points(world, image)
+        s.set_correspondences(pairs)
+        lin = s.linearize(thr, keep, want_status=True, n_pairs=len(pairs))
+        ref = oracle.linearize(K, rows, cols, pose, world, image, pairs, thr, keep, accum="f64")
+        s.close()
+        tag = f"seed {seed} case {case} n {len(pairs)} scale {scale:g} general {general} thr {thr:g} keep {keep}"
+        assert np.array_equal(lin["status"], ref["status"]), tag
+        assert lin["n_inliers"] == ref["n_inliers"], tag
+        with np.errstate(all="ignore"):
+            hs, bs = np.abs(ref["H"]).max(), np.abs(ref["b"]).max()
+        if np.isfinite(hs) and np.isfinite(bs):
+            assert np.abs(lin["H"] - ref["H"]).max() <= 1e-4 * hs, tag
+            assert np.abs(lin["b"] - ref["b"]).max() <= 1e-4 * max(bs, 1e-30), tag
+        else:  # an inlier with non-finite terms poisons the system in the reference; it must do so here too
+            assert not (np.isfinite(lin["H"]).all() and np.isfinite(lin["b"]).all()), tag
+
+
 def test_mask_on_threshold_knife_edge(ctx, oracle):
     """Measurements placed so that chi lands within a few ulps of the kernel threshold for EVERY
     correspondence: the inlier mask then depends on the last bit of the projection (the kernel's
