@@ -1227,7 +1227,8 @@ int vo_match_dev(vo_ctx* ctx, const float* d_descA, int64_t n1, const float* d_d
       // warps per 32-row group: enough to give every SM ~32 warps when the rows alone cannot
       const long long groups = (rows + 31) / 32;
       int n_warps = 1;
-      while (n_warps < kMaxScanWarps && groups * n_warps * 2 <= (long long)ctx->sm_count * 32) n_warps *= 2;
+      static const long long warp_budget = getenv("VO_MATCH_WARP_BUDGET") ? atoll(getenv("VO_MATCH_WARP_BUDGET")) : 32;
+      while (n_warps < kMaxScanWarps && groups * n_warps * 2 <= (long long)ctx->sm_count * warp_budget) n_warps *= 2;
       // magnitudes the filter's error analysis does not cover select the exact scan (flag read on the device)
       int* range_flag = (int*)(base + o_small + 32);
       static const bool force_exact = getenv("VO_MATCH_FORCE_EXACT") != nullptr;  // diagnostics: skip the filter
