@@ -106,56 +106,70 @@ __device__ __forceinline__ f2 prod2(f2 a, f2 b) { return fma2(a, b, 0ull); }
 // Two correspondences: exact part per point, then J, H += lambda J^T J and b += lambda J^T e in packed
 // f32x2 (lane 0 = first point, lane 1 = second; acc2[k] holds the two lanes' partial sums of slot k).
 // Points that do not contribute get all-zero Jacobian rows instead of a branch.
-template <bool KEEP, bool PINHOLE>
-__device__ __forceinline__ void picp_pair(const PicpCam& cam, const float* __restrict__ T, float thr,
-                                          float px0, float py0, float pz0, float zu0, float zv0,
-                                          float px1, float py1, float pz1, float zu1, float zv1, bool v0, bool v1,
-                                          f2 (&acc2)[29], int& n_in, int& n_out, int& st0, int& st1) {
-  // ---- exact part of BOTH points in packed f32x2 (camera.h:24-36, picp_solver.cpp:32-36,74).  Every
-  // product is rounded on its own (prod2 = fma with a +0 addend: ptxas would otherwise contract
-  // mul.rn.f32x2 + add.rn.f32x2 into FFMA2) and the additions follow Eigen's x0 + (x1 + x2) order, so each
-  // lane computes bit for bit what picp_project<> (vo_device.cuh) computes for one point.
+// state of a pair between the three stages below
+struct PairState {
   PointTerms t0, t1;
+  f2 c0, c1, c2, q0, q1, iz;
+  bool fix0, fix1;  // this lane needs the reference's arithmetic verbatim (general K, IEEE reciprocal)
+};
+
+// stage 1: c = R p + t and the pinhole shortcut values of q and 1/z for both lanes
+template <bool PINHOLE>
+__device__ __forceinline__ void pair_front(const PicpCam& cam, const float* __restrict__ T, float px0, float py0, float pz0,
+                                           float px1, float py1, float pz1, PairState& s) {
+  const f2 px = pack2(px0, px1), py = pack2(py0, py1), pz = pack2(pz0, pz1);
+  auto bc = [](float x) { return pack2(x, x); };
+  s.c0 = add2(bc(T[3]), add2(prod2(bc(T[0]), px), add2(prod2(bc(T[1]), py), prod2(bc(T[2]), pz))));
+  s.c1 = add2(bc(T[7]), add2(prod2(bc(T[4]), px), add2(prod2(bc(T[5]), py), prod2(bc(T[6]), pz))));
+  s.c2 = add2(bc(T[11]), add2(prod2(bc(T[8]), px), add2(prod2(bc(T[9]), py), prod2(bc(T[10]), pz))));
+  unpack2(s.c0, s.t0.c0, s.t1.c0);
+  unpack2(s.c1, s.t0.c1, s.t1.c1);
+  unpack2(s.c2, s.t0.c2, s.t1.c2);
+  s.q0 = 0ull; s.q1 = 0ull; s.iz = 0ull;
+  if (PINHOLE) {  // shortcut values for both lanes (see picp_project<> for why they are exact)
+    s.q0 = add2(prod2(bc(cam.K[0]), s.c0), prod2(bc(cam.K[2]), s.c2));
+    s.q1 = add2(prod2(bc(cam.K[4]), s.c1), prod2(bc(cam.K[5]), s.c2));
+    float r0, r1;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(s.t0.c2));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(s.t1.c2));
+    const f2 r = pack2(r0, r1);
+    s.iz = fma2(r, fma2(s.c2, pack2(-r0, -r1), bc(1.f)), r);
+  }
+  unpack2(s.q0, s.t0.q0, s.t1.q0);
+  unpack2(s.q1, s.t0.q1, s.t1.q1);
+  unpack2(s.iz, s.t0.iz, s.t1.iz);
+  const bool sc0 = PINHOLE && (s.t0.c2 >= 1e-30f) && (s.t0.c2 <= 1e30f) && finite_f(s.t0.c0) && finite_f(s.t0.c1);
+  const bool sc1 = PINHOLE && (s.t1.c2 >= 1e-30f) && (s.t1.c2 <= 1e30f) && finite_f(s.t1.c0) && finite_f(s.t1.c1);
+  s.fix0 = !sc0 && !(s.t0.c2 <= 0.f);
+  s.fix1 = !sc1 && !(s.t1.c2 <= 0.f);
+}
+
+// stage 2 (rare): the reference's arithmetic verbatim for the lanes that need it
+__device__ __forceinline__ void pair_fix(const PicpCam& cam, PairState& s) {
+  if (s.fix0) {
+    s.t0.q0 = dot3_rn(cam.K[0], s.t0.c0, cam.K[1], s.t0.c1, cam.K[2], s.t0.c2);
+    s.t0.q1 = dot3_rn(cam.K[3], s.t0.c0, cam.K[4], s.t0.c1, cam.K[5], s.t0.c2);
+    s.t0.iz = __frcp_rn(dot3_rn(cam.K[6], s.t0.c0, cam.K[7], s.t0.c1, cam.K[8], s.t0.c2));
+  }
+  if (s.fix1) {
+    s.t1.q0 = dot3_rn(cam.K[0], s.t1.c0, cam.K[1], s.t1.c1, cam.K[2], s.t1.c2);
+    s.t1.q1 = dot3_rn(cam.K[3], s.t1.c0, cam.K[4], s.t1.c1, cam.K[5], s.t1.c2);
+    s.t1.iz = __frcp_rn(dot3_rn(cam.K[6], s.t1.c0, cam.K[7], s.t1.c1, cam.K[8], s.t1.c2));
+  }
+  s.q0 = pack2(s.t0.q0, s.t1.q0);
+  s.q1 = pack2(s.t0.q1, s.t1.q1);
+  s.iz = pack2(s.t0.iz, s.t1.iz);
+}
+
+// stage 3: u, inside test, error, chi, status; then J, H += lambda J^T J and b += lambda J^T e
+template <bool KEEP, bool PINHOLE>
+__device__ __forceinline__ void pair_back(const PicpCam& cam, float thr, PairState& s, float zu0, float zv0, float zu1,
+                                          float zv1, bool v0, bool v1, f2 (&acc2)[29], int& n_in, int& n_out, int& st0,
+                                          int& st1) {
+  PointTerms& t0 = s.t0;
+  PointTerms& t1 = s.t1;
   {
-    const f2 px = pack2(px0, px1), py = pack2(py0, py1), pz = pack2(pz0, pz1);
-    auto bc = [](float x) { return pack2(x, x); };
-    const f2 c0 = add2(bc(T[3]), add2(prod2(bc(T[0]), px), add2(prod2(bc(T[1]), py), prod2(bc(T[2]), pz))));
-    const f2 c1 = add2(bc(T[7]), add2(prod2(bc(T[4]), px), add2(prod2(bc(T[5]), py), prod2(bc(T[6]), pz))));
-    const f2 c2 = add2(bc(T[11]), add2(prod2(bc(T[8]), px), add2(prod2(bc(T[9]), py), prod2(bc(T[10]), pz))));
-    unpack2(c0, t0.c0, t1.c0);
-    unpack2(c1, t0.c1, t1.c1);
-    unpack2(c2, t0.c2, t1.c2);
-    f2 q0 = 0ull, q1 = 0ull, iz = 0ull;
-    if (PINHOLE) {  // shortcut values for both lanes (see picp_project<> for why they are exact)
-      q0 = add2(prod2(bc(cam.K[0]), c0), prod2(bc(cam.K[2]), c2));
-      q1 = add2(prod2(bc(cam.K[4]), c1), prod2(bc(cam.K[5]), c2));
-      float r0, r1;
-      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(t0.c2));
-      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(t1.c2));
-      const f2 r = pack2(r0, r1);
-      iz = fma2(r, fma2(c2, pack2(-r0, -r1), bc(1.f)), r);
-    }
-    unpack2(q0, t0.q0, t1.q0);
-    unpack2(q1, t0.q1, t1.q1);
-    unpack2(iz, t0.iz, t1.iz);
-    const bool sc0 = PINHOLE && (t0.c2 >= 1e-30f) && (t0.c2 <= 1e30f) && finite_f(t0.c0) && finite_f(t0.c1);
-    const bool sc1 = PINHOLE && (t1.c2 >= 1e-30f) && (t1.c2 <= 1e30f) && finite_f(t1.c0) && finite_f(t1.c1);
-    if ((!sc0 && !(t0.c2 <= 0.f)) || (!sc1 && !(t1.c2 <= 0.f))) {
-      // rare: the reference's arithmetic verbatim (general K, IEEE reciprocal) for the lane that needs it
-      if (!sc0 && !(t0.c2 <= 0.f)) {
-        t0.q0 = dot3_rn(cam.K[0], t0.c0, cam.K[1], t0.c1, cam.K[2], t0.c2);
-        t0.q1 = dot3_rn(cam.K[3], t0.c0, cam.K[4], t0.c1, cam.K[5], t0.c2);
-        t0.iz = __frcp_rn(dot3_rn(cam.K[6], t0.c0, cam.K[7], t0.c1, cam.K[8], t0.c2));
-      }
-      if (!sc1 && !(t1.c2 <= 0.f)) {
-        t1.q0 = dot3_rn(cam.K[0], t1.c0, cam.K[1], t1.c1, cam.K[2], t1.c2);
-        t1.q1 = dot3_rn(cam.K[3], t1.c0, cam.K[4], t1.c1, cam.K[5], t1.c2);
-        t1.iz = __frcp_rn(dot3_rn(cam.K[6], t1.c0, cam.K[7], t1.c1, cam.K[8], t1.c2));
-      }
-      q0 = pack2(t0.q0, t1.q0);
-      q1 = pack2(t0.q1, t1.q1);
-      iz = pack2(t0.iz, t1.iz);
-    }
+    const f2 q0 = s.q0, q1 = s.q1, iz = s.iz;
     const f2 u = prod2(q0, iz), v = prod2(q1, iz);
     float u0, u1, w0, w1;
     unpack2(u, u0, u1);
@@ -413,10 +427,17 @@ __global__ void __launch_bounds__(kLinThreads, kCtasPerSm) picp_linearize_kernel
       if (!any) continue;
       int s0, s1, s2, s3;
       const long long left = a.n - base;  // >= 1; < 4 only in the last quad of the stream
-      picp_pair<KEEP, PINHOLE>(a.cam, T, a.thr, wx.x, wy.x, wz.x, zu.x, zv.x, wx.y, wy.y, wz.y, zu.y, zv.y, true, left > 1,
-                               acc2, n_in, n_out, s0, s1);
-      picp_pair<KEEP, PINHOLE>(a.cam, T, a.thr, wx.z, wy.z, wz.z, zu.z, zv.z, wx.w, wy.w, wz.w, zu.w, zv.w, left > 2,
-                               left > 3, acc2, n_in, n_out, s2, s3);
+      // both pairs of the quad go through the stages together: one (rare) branch for the four points, and the
+      // select-heavy tail of one pair sits in the same basic block as the FFMA2-heavy accumulation of the other
+      PairState pa, pb;
+      pair_front<PINHOLE>(a.cam, T, wx.x, wy.x, wz.x, wx.y, wy.y, wz.y, pa);
+      pair_front<PINHOLE>(a.cam, T, wx.z, wy.z, wz.z, wx.w, wy.w, wz.w, pb);
+      if (pa.fix0 || pa.fix1 || pb.fix0 || pb.fix1) {
+        pair_fix(a.cam, pa);
+        pair_fix(a.cam, pb);
+      }
+      pair_back<KEEP, PINHOLE>(a.cam, a.thr, pa, zu.x, zv.x, zu.y, zv.y, true, left > 1, acc2, n_in, n_out, s0, s1);
+      pair_back<KEEP, PINHOLE>(a.cam, a.thr, pb, zu.z, zv.z, zu.w, zv.w, left > 2, left > 3, acc2, n_in, n_out, s2, s3);
       if (STATUS) {
         if (base + 3 < a.n) {
           *reinterpret_cast<uchar4*>(a.status + base) = make_uchar4(s0, s1, s2, s3);
