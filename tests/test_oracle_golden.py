@@ -112,3 +112,76 @@ def test_replay_full_oracle(oracle, dataset):
     assert dxy <= 0.01 * 41.4, dxy
     assert dth <= 0.015, dth
     assert derr <= 0.05, derr
+
+
+def _numpy_match_rows(A, B):
+    """match_points' per-row (best, second, idx) restated a second time, independently of oracle/vo_oracle.cpp: numpy
+    float32 arithmetic (every operation rounded once), Eigen's squaredNorm order for 10 coefficients
+    and the sequential update rule of my_utilities.h:93-99 (strict comparisons, first index wins, NaN / inf ignored)."""
+    FLT_MAX = np.finfo(np.float32).max
+    with np.errstate(all="ignore"):
+        d = A[:, None, :] - B[None, :, :]
+        x = d * d
+        s = ((x[..., 0] + x[..., 4]) + (x[..., 2] + x[..., 6])) + ((x[..., 1] + x[..., 5]) + (x[..., 3] + x[..., 7]))
+        s = (s + x[..., 8]) + x[..., 9]
+    assert s.dtype == np.float32
+    usable = s < FLT_MAX                      # NaN and values >= FLT_MAX never pass `d < best`
+    key = np.where(usable, s, np.float32(np.inf))
+    idx = np.argmin(key, axis=1)              # first minimum
+    best = key[np.arange(len(A)), idx]
+    none = ~usable.any(axis=1)
+    masked = key.copy()
+    masked[np.arange(len(A)), idx] = np.inf
+    second = masked.min(axis=1)
+    best = np.where(none, FLT_MAX, best).astype(np.float32)
+    second = np.where(np.isinf(second), FLT_MAX, second).astype(np.float32)
+    return best, second, np.where(none, -1, idx).astype(np.int32)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_oracle_matcher_against_an_independent_numpy_restatement(oracle, seed):
+    """the oracle is what the CUDA matcher is compared with bit for bit; here it is itself compared bit for bit with a
+    second restatement on adversarial sets (ties, zero distances, huge / tiny scales, offsets, NaN, inf)"""
+    import synth
+    rng = np.random.default_rng(seed)
+    for kind in ("uniform", "clustered", "lattice", "lowrank", "cauchy"):
+        A, B = synth.stress_descriptors(rng, kind, int(rng.integers(1, 300)), int(rng.integers(1, 700)))
+        if rng.random() < 0.5:
+            A[rng.integers(0, len(A)), rng.integers(0, 10)] = np.nan
+            B[rng.integers(0, len(B)), rng.integers(0, 10)] = np.inf
+        _, _, best, second, idx = oracle.match(A, B, want_rows=True)
+        nb, ns, ni = _numpy_match_rows(A, B)
+        assert np.array_equal(idx, ni), kind
+        assert np.array_equal(best.view(np.uint32), nb.view(np.uint32)), kind
+        assert np.array_equal(second.view(np.uint32), ns.view(np.uint32)), kind
+
+
+def _numpy_picp_status(K, rows, cols, pose, world, image, pairs, thr):
+    """Camera::projectPoint + the chi test of PICPSolver::linearize (camera.h:24-36, picp_solver.cpp:65-80) restated a
+    second time in numpy float32: length-3 products reduce as x0 + (x1 + x2), the reciprocal is formed in double and
+    rounded to float, every comparison keeps the reference's NaN behaviour (a NaN never leaves the image)."""
+    f = np.float32
+    K = K.astype(f); T = pose.astype(f)
+    p = world[pairs[:, 1]].astype(f); z = image[pairs[:, 0]].astype(f)
+    with np.errstate(all="ignore"):
+        dot3 = lambda a0, b0, a1, b1, a2, b2: (a0 * b0 + (a1 * b1 + a2 * b2)).astype(f)
+        c = [(T[i, 3] + dot3(T[i, 0], p[:, 0], T[i, 1], p[:, 1], T[i, 2], p[:, 2])).astype(f) for i in range(3)]
+        q = [dot3(K[i, 0], c[0], K[i, 1], c[1], K[i, 2], c[2]) for i in range(3)]
+        iz = (1.0 / q[2].astype(np.float64)).astype(f)
+        u, v = (q[0] * iz).astype(f), (q[1] * iz).astype(f)
+        outside = (c[2] <= 0) | (u < 0) | (u > f(cols - 1)) | (v < 0) | (v > f(rows - 1))
+        e0, e1 = (u - z[:, 0]).astype(f), (v - z[:, 1]).astype(f)
+        chi = (e0 * e0 + e1 * e1).astype(f)
+        st = np.where(outside, 0, np.where(chi > f(thr), 2, 1)).astype(np.uint8)  # VO_PICP_SKIPPED / OUTLIER / INLIER
+    return st
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_oracle_picp_status_against_an_independent_numpy_restatement(oracle, seed):
+    import synth
+    rng = np.random.default_rng(seed)
+    for _ in range(8):
+        K, rows, cols, pose, world, image, pairs, thr, keep, general, scale = synth.picp_stress_case(rng)
+        ref = oracle.linearize(K, rows, cols, pose, world, image, pairs, thr, keep, accum="f64")
+        st = _numpy_picp_status(K, rows, cols, pose, world, image, pairs, thr)
+        assert np.array_equal(ref["status"], st), (len(pairs), scale, general, thr)
