@@ -284,35 +284,42 @@ __device__ void picp_solve_update(const double* __restrict__ res, float damping,
 }
 
 // ------------------------------------------------------------------ fused all-reduce over NVLink peer memory
-// One warp. Lane c owns term c. Push my 32 terms into every rank's mailbox (mine included), publish a
-// flag with release semantics, wait for every rank's flag, then sum the slots in RANK order: all ranks
-// add the same numbers in the same order, so they solve bit-identical systems without a broadcast.
+// One warp. Lane c owns term c. Push my 32 terms into every rank's mailbox (mine included) as self-validating
+// 8-byte words {half of the double | sequence number}, poll my own mailbox until every rank's words carry this
+// round's number, and sum them in RANK order: all ranks add the same numbers in the same order, so they solve
+// bit-identical systems without a broadcast.  (A first version wrote plain doubles, a system-scope fence, a flag
+// per rank and a second fence before reading: ~6.5 us per round; see profiles/r01_final_summary.md.)
 // Mailboxes are double-buffered by round parity; a rank can reach round s+2 only after every rank has
 // published s+1, i.e. finished reading round s, so a parity buffer is never overwritten while in use.
 __device__ __forceinline__ double picp_peer_allreduce(const LinArgs& a, double mine, int lane) {
   VoMailbox* me = a.peers[a.peer_rank];
   const unsigned seq = *(volatile unsigned*)&me->seq + 1u;  // this round's sequence number (same on all ranks)
   const int par = (int)(seq & 1u);
-  for (int p = 0; p < a.peer_n; ++p) a.peers[p]->slots[par][a.peer_rank][lane] = mine;  // 256 B per peer
-  __threadfence_system();
-  __syncwarp();
-  if (lane < a.peer_n) *(volatile unsigned*)&a.peers[lane]->flags[par][a.peer_rank] = seq;
-  // lane q waits for rank q's flag (all peers in parallel), then ONE system-scope fence orders the slot reads
+  const unsigned long long bits = (unsigned long long)__double_as_longlong(mine), tag = (unsigned long long)seq << 32;
+  const unsigned long long w0 = (bits & 0xffffffffull) | tag, w1 = (bits >> 32) | tag;
+  for (int p = 0; p < a.peer_n; ++p) {  // 512 B per peer, every 8-byte word self-validating
+    volatile unsigned long long* dst = &a.peers[p]->ll[par][a.peer_rank][lane][0];
+    dst[0] = w0;
+    dst[1] = w1;
+  }
+  // lane c collects term c of every rank in RANK order as the words arrive
+  double total = 0.0;
   bool ok = true;
-  if (lane < a.peer_n) {
+  for (int q = 0; q < a.peer_n; ++q) {
+    const volatile unsigned long long* src = &me->ll[par][q][lane][0];
+    unsigned long long r0 = src[0], r1 = src[1];
     long long spins = 0;
-    while (*(volatile unsigned*)&me->flags[par][lane] != seq) {
+    while ((unsigned)(r0 >> 32) != seq || (unsigned)(r1 >> 32) != seq) {
       if (++spins > (1ll << 24)) {  // ~5 s: a peer never launched its round; flag it instead of hanging the GPU
         ok = false;
         break;
       }
+      r0 = src[0];
+      r1 = src[1];
     }
+    total += __longlong_as_double((long long)((r0 & 0xffffffffull) | (r1 << 32)));
   }
   ok = __all_sync(0xffffffffu, ok);
-  __threadfence_system();
-  double total = 0.0;
-  for (int q = 0; q < a.peer_n; ++q) total += *(volatile double*)&me->slots[par][q][lane];
-  __syncwarp();
   if (lane == 0) {
     *(volatile unsigned*)&me->seq = seq;
     if (!ok) me->timeout = 1u;

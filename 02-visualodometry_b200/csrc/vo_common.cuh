@@ -34,10 +34,11 @@ struct vo_ctx {
   int peer_rank = 0;
 };
 
-// mailbox layout: [2 parities][VO_MAX_PEERS ranks][32 doubles] + flags [2][VO_MAX_PEERS] + sequence counter
+// mailbox layout: [2 parities][VO_MAX_PEERS ranks][32 terms] x two 8-byte words {32 payload bits | sequence number << 32}
+// (a payload and its flag travel in ONE 8-byte store, which NVLink delivers atomically: no fence, no separate
+// flag write - the "LL" protocol), + the local sequence counter
 struct VoMailbox {
-  double slots[2][VO_MAX_PEERS][32];
-  unsigned flags[2][VO_MAX_PEERS];
+  unsigned long long ll[2][VO_MAX_PEERS][32][2];
   unsigned seq;       // rounds exchanged so far (advanced by the kernel)
   unsigned timeout;   // set by a kernel whose wait for a peer expired
 };
