@@ -185,3 +185,26 @@ def test_oracle_picp_status_against_an_independent_numpy_restatement(oracle, see
         ref = oracle.linearize(K, rows, cols, pose, world, image, pairs, thr, keep, accum="f64")
         st = _numpy_picp_status(K, rows, cols, pose, world, image, pairs, thr)
         assert np.array_equal(ref["status"], st), (len(pairs), scale, general, thr)
+
+
+def test_oracle_isometry_algebra_against_numpy_float32(oracle):
+    """Isometry3f inverse and product (exec/icp_test.cpp:79,114; Eigen: coefficient products reduced as x0 + (x1 + x2)),
+    restated in numpy float32 and compared bit for bit"""
+    f = np.float32
+    rng = np.random.default_rng(0)
+    dot3 = lambda a0, b0, a1, b1, a2, b2: f(f(a0 * b0) + f(f(a1 * b1) + f(a2 * b2)))
+    for _ in range(200):
+        scale = f(rng.choice([1e-3, 1.0, 50.0, 1e6]))
+        A = np.concatenate([rng.normal(0, 1, (3, 3)), rng.normal(0, 1, (3, 1)) * scale], 1).astype(f)
+        B = np.concatenate([rng.normal(0, 1, (3, 3)), rng.normal(0, 1, (3, 1)) * scale], 1).astype(f)
+        inv = np.zeros((3, 4), f)
+        for i in range(3):
+            inv[i, :3] = A[:3, i]
+            inv[i, 3] = dot3(-A[0, i], A[0, 3], -A[1, i], A[1, 3], -A[2, i], A[2, 3])
+        assert np.array_equal(oracle.pose_inverse(A).view(np.uint32), inv.view(np.uint32))
+        mul = np.zeros((3, 4), f)
+        for i in range(3):
+            for j in range(4):
+                mul[i, j] = dot3(A[i, 0], B[0, j], A[i, 1], B[1, j], A[i, 2], B[2, j])
+            mul[i, 3] = f(mul[i, 3] + A[i, 3])
+        assert np.array_equal(oracle.pose_mul(A, B).view(np.uint32), mul.view(np.uint32))
