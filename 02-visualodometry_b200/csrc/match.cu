@@ -1,22 +1,31 @@
-// match.cu — brute-force descriptor matching on sm_100a.
+// match.cu — descriptor matching on sm_100a.
 //
 // Replaces the header template match_points<P1,P2> (reference src/my_utilities.h:70-120):
 // for every query row i, best / second-best squared L2 distance over all rows j of the other
 // set, lowest index on ties, accepted iff best < 0.2 && best/second < 0.8.
 //
 // Layout: descriptors packed row-major float[N][D] (the shim gathers them out of the
-// reference's per-record heap VectorXf).  Work decomposition:
-//   grid.x = query-row blocks (one row per thread: its D floats live in registers)
-//   grid.y = column splits of the other set, sized so the grid fills whole waves of SMs
-//   each CTA streams its column range through shared memory in tiles (rows padded to a
-//   multiple of 4 floats -> conflict-free broadcast LDS.128)
-// followed by an exact merge of the per-split (best, second, idx) triples in split order, the
-// threshold/ratio test and a stable (ascending i) compaction.
+// reference's per-record heap VectorXf).
 //
-// Rounding contract: the distance is evaluated in float32 with explicit round-to-nearest
-// sub/mul/add in the order Eigen's SSE squaredNorm redux uses for VectorXf;
-// nothing is contracted to FMA, so indices and accept flags are bit-exact against the oracle.
-// This is FP32-issue bound (30 flop per pair, D = 10): no tensor cores, see DESIGN.md.
+// Rounding contract: every distance that decides a result is evaluated in float32 with explicit
+// round-to-nearest sub/mul/add in the order Eigen's SSE squaredNorm redux uses for VectorXf
+// (SURVEY App. A.7); nothing is contracted to FMA, so best, second-best, indices and accept flags
+// are bit-exact against the oracle on every path.
+//
+// Three paths (vo_match_dev picks by size; all end in the same merge / accept test / stable compaction):
+//   1. match_scan_kernel<D>, D = 1..16, any size: one query row per thread (its D floats in registers),
+//      grid.y = column splits sized so the grid fills whole waves, columns streamed through shared memory
+//      in tiles; exact merge of the per-split (best, second, idx) triples in split order.  This is what
+//      the frame loop uses (500 x 490 descriptors).
+//   2. match_scan10_kernel, D = 10, >= 8192 rows: rows visited in Morton order, two columns per packed
+//      f32x2 instruction, and an exact monotone lower bound (first half of Eigen's reduction tree) voted
+//      across the warp before the second half is evaluated.
+//   3. match_scan10_mma_kernel (+ match_scan10_indexed_kernel as its exact twin), D = 10, >= 8192
+//      columns and enough work: rows and columns sorted on one Morton curve, 128-column tiles with
+//      bounding boxes in two levels, tiles skipped by a per-row point-to-box bound, and inside a visited
+//      tile a bf16 tensor-core filter (mma.sync m16n8k16: |a|^2 + |b|^2 - 2 a.b - bound, scaled so that it
+//      is a guaranteed lower bound of the reference's float distance) that leaves a handful of columns
+//      per row for the exact fp32 evaluation.  Derivation and the error budget: at the kernel.
 #include "vo_device.cuh"
 
 #include <float.h>
