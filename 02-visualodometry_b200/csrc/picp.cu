@@ -24,8 +24,12 @@
 // assignment -> warp shuffle tree -> shared-memory sum over warps in warp order ->
 // per-block partial; the block that takes the last ticket sums the partials in block order
 // in float64 (pass 2), then (single GPU) solves the damped 6x6 system and updates the pose
-// in the same launch.  With a communicator, pass 2 stops at `result`, NCCL all-reduces the
-// 32 doubles over NVLink, and a one-warp kernel solves identically on every rank.
+// in the same launch.  With peers attached (vo_ctx_peer_attach) the same block first exchanges the 32
+// sums with the other GPUs through IPC-mapped mailboxes (picp_peer_allreduce: self-validating 8-byte
+// words over NVLink, summed in rank order) and every rank solves the identical system; with only an
+// NCCL communicator, pass 2 stops at `result`, ncclAllReduce runs on the stream and a one-warp kernel solves.
+// Rounds of a frame are chained with programmatic dependent launch (prologue + first tiles of round r+1 under
+// the tail of round r).
 //
 // Rounding contract: everything that decides the inlier mask (camera point, projection,
 // reciprocal, error, chi) uses explicit round-to-nearest intrinsics in the reference's
