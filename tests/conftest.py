@@ -25,6 +25,12 @@ def cv2fx():
 
 
 @pytest.fixture(scope="session")
+def cv2tri():
+    """cv2.triangulatePoints on 24 adversarial two-view problems (oracle/gen_golden_tri.py)"""
+    return np.load(os.path.join(ROOT, "tests", "golden", "cv2_triangulate.npz"))
+
+
+@pytest.fixture(scope="session")
 def oracle():
     from oracle import pyoracle
     pyoracle.build()

@@ -83,3 +83,21 @@ def test_anti_join(ctx, oracle):
         m = rng.integers(0, 150, nm).astype(np.int32)
         c = rng.integers(0, 150, nc).astype(np.int32)
         assert np.array_equal(ctx.anti_join(m, c), oracle.anti_join(m, c))
+
+
+def test_triangulate_vs_cv2_on_adversarial_two_view_problems(ctx, oracle, cv2tri):
+    """same fixtures as tests/test_oracle_golden.py: the CUDA DLT against cv2 4.13 (bulk of every case at float32
+    output precision) and against the oracle (1e-5 of the extent on the points both resolve)"""
+    K = cv2tri["K"]
+    for c in range(int(cv2tri["n_cases"])):
+        T1, T2, x1, x2 = cv2tri[f"c{c}_T1"], cv2tri[f"c{c}_T2"], cv2tri[f"c{c}_x1"], cv2tri[f"c{c}_x2"]
+        X = ctx.triangulate(K, T1, T2, x1, x2)
+        R, X4 = cv2tri[f"c{c}_X3"], cv2tri[f"c{c}_X4"]
+        with np.errstate(all="ignore"):
+            rel = np.abs(X - R).max(1) / np.maximum(np.abs(R).max(1), 1e-30)
+            ok = np.isfinite(rel) & (np.abs(X4[:, 3]) >= 1e-4 * np.abs(X4).max(1))
+        assert np.median(rel[ok]) <= 1e-4 and np.quantile(rel[ok], 0.9) <= 2e-3, (c, cv2tri[f"c{c}_cfg"])
+        Xo = oracle.triangulate(K, T1, T2, x1, x2)
+        with np.errstate(all="ignore"):
+            relo = np.abs(X - Xo).max(1) / np.maximum(np.abs(Xo).max(1), 1e-30)
+        assert np.median(relo[ok]) <= 1e-5, (c, cv2tri[f"c{c}_cfg"], float(np.median(relo[ok])))
