@@ -31,6 +31,12 @@ def cv2tri():
 
 
 @pytest.fixture(scope="session")
+def cv2pose():
+    """cv2.findEssentialMat(RANSAC) + recoverPose on 20 synthetic two-view problems (oracle/gen_golden_pose.py)"""
+    return np.load(os.path.join(ROOT, "tests", "golden", "cv2_recoverpose.npz"))
+
+
+@pytest.fixture(scope="session")
 def oracle():
     from oracle import pyoracle
     pyoracle.build()

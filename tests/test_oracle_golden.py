@@ -230,3 +230,19 @@ def test_triangulate_vs_cv2_on_adversarial_two_view_problems(oracle, cv2tri):
         X = oracle.triangulate(K, cv2tri[f"c{c}_T1"], cv2tri[f"c{c}_T2"], cv2tri[f"c{c}_x1"], cv2tri[f"c{c}_x2"])
         med, q90 = _tri_stats(X, cv2tri[f"c{c}_X3"], cv2tri[f"c{c}_X4"])
         assert med <= 1e-4 and q90 <= 2e-3, (c, cv2tri[f"c{c}_cfg"], med, q90)
+
+
+def test_recover_pose_matches_cv2_on_more_motions(oracle, cv2pose):
+    """sideways / forward / backward baselines, rotations up to ~0.5 rad, 0..1 px noise, 10 % gross outliers,
+    20..400 points: given cv2's E, the restated decomposeEssentialMat + cheirality vote returns cv2's R, t, mask
+    and inlier count (src/cam.cpp:61)"""
+    K = cv2pose["K"]
+    for c in range(int(cv2pose["n_cases"])):
+        E = cv2pose[f"c{c}_E"]
+        if not E.any():
+            continue
+        R, t, mask, good = oracle.recover_pose(E, K, cv2pose[f"c{c}_x1"], cv2pose[f"c{c}_x2"])
+        assert np.abs(R - cv2pose[f"c{c}_R"]).max() < 1e-12, c
+        assert np.abs(t - cv2pose[f"c{c}_t"]).max() < 1e-12, c
+        assert np.array_equal(mask > 0, cv2pose[f"c{c}_mask"] > 0), c
+        assert int(good) == int(cv2pose[f"c{c}_good"]), c
