@@ -25,19 +25,6 @@ inline const float FRAMES_DISTANCE_THRESHOLD = 0.1f;
 inline const float RATIO_THRESHOLD = 0.8f;
 inline const int PICP_RUNS = 10;
 
-namespace vo {
-// descriptor matrix + ids of a record vector, packed for the device
-template <typename P>
-void pack_records(const std::vector<P>& pts, int dim, std::vector<float>& desc, std::vector<int32_t>& ids) {
-  desc.resize(pts.size() * (size_t)dim);
-  ids.resize(pts.size());
-  for (size_t i = 0; i < pts.size(); ++i) {
-    for (int k = 0; k < dim; ++k) desc[i * dim + k] = pts[i].descriptor[k];
-    ids[i] = pts[i].id_real;
-  }
-}
-}  // namespace vo
-
 // Brute-force descriptor matching with ratio test (src/my_utilities.h:70-120). Appends to `matches`
 // and `correspondences` (never clears), ascending in the index of points1, and prints the reference's
 // summary line. For image<->world matching pass the image points first.
@@ -50,8 +37,10 @@ void match_points(const std::vector<PointType1>& points1, const std::vector<Poin
     const int dim = (int)points1[0].descriptor.size();
     std::vector<float> dA, dB;
     std::vector<int32_t> iA, iB;
-    vo::pack_records(points1, dim, dA, iA);
-    vo::pack_records(points2, dim, dB, iB);
+    vo::gather_descriptors(points1, dA);  // vo_records.h: row-major float[N][D] + the id_real column
+    vo::gather_descriptors(points2, dB);
+    vo::gather_real_ids(points1, iA);
+    vo::gather_real_ids(points2, iB);
     std::vector<int32_t> pairs(2 * points1.size());
     int64_t n = 0, stats[2] = {0, 0};
     vo::check(vo_match(vo::default_ctx(), dA.data(), (int64_t)points1.size(), dB.data(), (int64_t)points2.size(), dim,
