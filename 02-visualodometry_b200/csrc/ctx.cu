@@ -70,6 +70,7 @@ int vo_ctx_destroy(vo_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   if (ctx->mailbox) cudaFree(ctx->mailbox);
   if (ctx->scratch) cudaFree(ctx->scratch);
+  if (ctx->stage) cudaFree(ctx->stage);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -134,6 +135,21 @@ int vo_scratch(vo_ctx* ctx, size_t bytes, void** out) {
     ctx->scratch_bytes = want;
   }
   *out = ctx->scratch;
+  return VO_OK;
+}
+
+int vo_stage(vo_ctx* ctx, size_t bytes, void** out) {
+  if (bytes > ctx->stage_bytes) {
+    VO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->stage) cudaFree(ctx->stage);
+    ctx->stage = nullptr;
+    ctx->stage_bytes = 0;
+    size_t want = vo_align_up(bytes + bytes / 4, 1 << 20);
+    cudaError_t e = cudaMalloc(&ctx->stage, want);
+    if (e != cudaSuccess) return vo_set_error(ctx, VO_ERR_NOMEM, "cudaMalloc(stage)", cudaGetErrorString(e));
+    ctx->stage_bytes = want;
+  }
+  *out = ctx->stage;
   return VO_OK;
 }
 

@@ -1330,22 +1330,21 @@ int vo_match(vo_ctx* ctx, const float* descA, int64_t n1, const float* descB, in
   const size_t bIA = ids ? (size_t)rows * 4 : 0, bIB = ids ? (size_t)n2 * 4 : 0, bP = (size_t)rows * 8;
   float *dA = nullptr, *dB = nullptr;
   int32_t *dIA = nullptr, *dIB = nullptr, *dP = nullptr;
-  cudaError_t e = cudaMalloc((void**)&dA, bA ? bA : 4);
-  if (e == cudaSuccess) e = cudaMalloc((void**)&dB, bB ? bB : 4);
-  if (e == cudaSuccess && ids) e = cudaMalloc((void**)&dIA, bIA ? bIA : 4);
-  if (e == cudaSuccess && ids) e = cudaMalloc((void**)&dIB, bIB ? bIB : 4);
-  if (e == cudaSuccess) e = cudaMalloc((void**)&dP, bP);
-  auto cleanup = [&]() {
-    if (dA) cudaFree(dA);
-    if (dB) cudaFree(dB);
-    if (dIA) cudaFree(dIA);
-    if (dIB) cudaFree(dIB);
-    if (dP) cudaFree(dP);
-  };
-  if (e != cudaSuccess) {
-    cleanup();
-    return vo_set_error(ctx, VO_ERR_NOMEM, "vo_match: cudaMalloc", cudaGetErrorString(e));
+  // one staging arena per context (grown on demand, reused): no cudaMalloc / cudaFree per call
+  char* stage;
+  {
+    const size_t oA = 0, oB = vo_align_up(oA + bA, 256), oIA = vo_align_up(oB + bB, 256), oIB = vo_align_up(oIA + bIA, 256);
+    const size_t oP = vo_align_up(oIB + bIB, 256), total = oP + bP + 256;
+    st = vo_stage(ctx, total, (void**)&stage);
+    if (st) return st;
+    dA = (float*)(stage + oA);
+    dB = (float*)(stage + oB);
+    dIA = ids ? (int32_t*)(stage + oIA) : nullptr;
+    dIB = ids ? (int32_t*)(stage + oIB) : nullptr;
+    dP = (int32_t*)(stage + oP);
   }
+  auto cleanup = [&]() {};
+  cudaError_t e;
   e = cudaMemcpyAsync(dA, descA + row_begin * dim, bA, cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess && bB) e = cudaMemcpyAsync(dB, descB, bB, cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess && ids) e = cudaMemcpyAsync(dIA, idA + row_begin, bIA, cudaMemcpyHostToDevice, ctx->stream);

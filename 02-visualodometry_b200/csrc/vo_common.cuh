@@ -20,6 +20,10 @@ struct vo_ctx {
   // scratch arena (device) reused by the stateless entry points; grows monotonically
   void* scratch = nullptr;
   size_t scratch_bytes = 0;
+  // device staging of the host-buffer entry points (vo_match): a second arena, because the *_dev call underneath
+  // carves its own scratch while the staged inputs are still in use
+  void* stage = nullptr;
+  size_t stage_bytes = 0;
   // pinned host staging for small synchronous read-backs
   void* pinned = nullptr;
   size_t pinned_bytes = 0;
@@ -65,6 +69,7 @@ int vo_set_error(vo_ctx* ctx, int status, const char* what, const char* detail);
 
 // device scratch of at least `bytes` (256-B aligned), valid until the next vo_scratch call
 int vo_scratch(vo_ctx* ctx, size_t bytes, void** out);
+int vo_stage(vo_ctx* ctx, size_t bytes, void** out);
 int vo_pinned(vo_ctx* ctx, size_t bytes, void** out);
 int vo_ctx_activate(vo_ctx* ctx);
 
