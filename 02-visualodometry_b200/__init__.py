@@ -89,6 +89,9 @@ _sig("vo_picp_set_points", C.c_int, _vp, _vp, _i64, _vp, _i64)
 _sig("vo_picp_set_points_dev", C.c_int, _vp, _vp, _i64, _vp, _i64)
 _sig("vo_picp_set_correspondences", C.c_int, _vp, _vp, _i64)
 _sig("vo_picp_set_correspondences_dev", C.c_int, _vp, _vp, _i64)
+_sig("vo_picp_set_mode", C.c_int, _vp, C.c_int)
+_sig("vo_picp_pack", C.c_int, _vp)
+_sig("vo_picp_resident_capacity", C.c_int, _vp, C.POINTER(_i64))
 _sig("vo_picp_linearize", C.c_int, _vp, _f, C.c_int, _vp, _vp, C.POINTER(Stats), _vp)
 _sig("vo_picp_one_round", C.c_int, _vp, _f, _f, C.c_int, C.POINTER(Stats))
 _sig("vo_picp_enqueue_rounds", C.c_int, _vp, _f, _f, C.c_int, C.c_int)
@@ -98,6 +101,8 @@ _sig("vo_match", C.c_int, _vp, _vp, _i64, _vp, _i64, C.c_int, _f, _f, _vp, _vp, 
      C.POINTER(_i64), _vp)
 _sig("vo_match_dev", C.c_int, _vp, _vp, _i64, _vp, _i64, C.c_int, _f, _f, _vp, _vp, _i64, _i64, _vp, _i64,
      C.POINTER(_i64), _vp, _vp, _vp, _vp)
+_sig("vo_match_set_path", C.c_int, _vp, C.c_int)
+_sig("vo_selftest_reciprocal", C.c_int, _vp, _vp)
 _sig("vo_triangulate", C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp)
 _sig("vo_triangulate_dev", C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp)
 _sig("vo_essential_recover", C.c_int, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, C.POINTER(C.c_int))
@@ -110,6 +115,7 @@ _sig("vo_seq_batch_run_dev", C.c_int, _vp, C.POINTER(SeqParams), C.c_int, C.c_in
 from .sharding import N_TERMS, pack_terms, shard_bounds, shard_range, unpack_terms  # noqa: E402,F401
 
 MAX_ROUNDS = 64
+MODE_AUTO, MODE_STREAM, MODE_RESIDENT = 0, 1, 2
 STATUS_SKIPPED, STATUS_INLIER, STATUS_OUTLIER = 0, 1, 2
 
 
@@ -231,6 +237,13 @@ class Context:
     def picp(self):
         return Picp(self)
 
+    def selftest_reciprocal(self):
+        """all 2^32 inputs of the reciprocal shortcut vs __frcp_rn: (inputs in the gate, packed mismatches,
+        scalar mismatches, first bad bit pattern + 1)"""
+        out = np.zeros(4, np.uint64)
+        self._check(_L.vo_selftest_reciprocal(self._h, _p(out)), "vo_selftest_reciprocal")
+        return tuple(int(x) for x in out)
+
     # ---- pr::Camera
     def project_points(self, K, rows, cols, pose, world, keep_indices=False):
         world = _f32(world).reshape(-1, 3)
@@ -242,6 +255,11 @@ class Context:
         return out[: n_out.value].copy(), n_in.value
 
     # ---- match_points
+    MATCH_AUTO, MATCH_BRUTE, MATCH_ORDERED, MATCH_INDEXED_EXACT, MATCH_INDEXED_FILTERED = 0, 1, 2, 3, 4
+
+    def match_set_path(self, path):
+        self._check(_L.vo_match_set_path(self._h, int(path)), "vo_match_set_path")
+
     def match(self, descA, descB, dist_thr=0.2, ratio_thr=0.8, idA=None, idB=None, row_begin=0, row_end=None):
         descA = _f32(descA)
         descB = _f32(descB)
@@ -392,6 +410,20 @@ class Picp:
     def set_correspondences_dev(self, d_pairs, n):
         self.ctx._check(_L.vo_picp_set_correspondences_dev(self._h, _vp(d_pairs), n),
                         "vo_picp_set_correspondences_dev")
+
+    def pack(self):
+        self.ctx._check(_L.vo_picp_pack(self._h), "vo_picp_pack")
+
+    def set_mode(self, mode):
+        """MODE_AUTO / MODE_STREAM (one launch per round over the packed planes) / MODE_RESIDENT (one persistent
+        launch per solve, correspondences resident in shared memory)"""
+        self.ctx._check(_L.vo_picp_set_mode(self._h, int(mode)), "vo_picp_set_mode")
+
+    @property
+    def resident_capacity(self):
+        n = _i64(0)
+        self.ctx._check(_L.vo_picp_resident_capacity(self._h, C.byref(n)), "vo_picp_resident_capacity")
+        return n.value
 
     def linearize(self, thr, keep_outliers=False, want_status=False, n_pairs=None):
         H = np.zeros(36, np.float32)

@@ -627,6 +627,8 @@ __device__ __forceinline__ float min3(float a, float b, float c) {  // FMNMX3; N
 #ifndef VO_MMA_BUFS
 #define VO_MMA_BUFS 1
 #endif
+constexpr int kDenseMinPerRow = 48;  // survivors of one row in a 128-column tile from which the outright scan is cheaper
+constexpr int kDenseSkip = 7;        // tiles evaluated outright after a dense one before the filter is tried again
 constexpr int kFragBufs = VO_MMA_BUFS;             // tile fragment buffers per warp (TMA bulk copies in flight)
 constexpr int kFragTileBytes = kTileRows * 32;     // 128 columns x 16 bf16
 constexpr int kMmaWarpSmem = 2048 + kFragBufs * kFragTileBytes + 64;
@@ -715,6 +717,7 @@ __global__ void __launch_bounds__(VO_MMA_LB) match_scan10_mma_kernel(
   }
   float best = FLT_MAX, second = FLT_MAX, bound = FLT_MAX;
   int idx = -1;
+  int dense_skip = 0;  // tiles still to be evaluated outright before the filter is probed again (warp-uniform)
   // The rows' bounds ride in the A operand (k = 14,15, held by the threads with tq == 3): the MMA output is v - bound,
   // a column survives iff its output is <= 0, and a running 3-input minimum over 4 column blocks needs one
   // comparison.  (The bound joins the sum as two more terms; if it dwarfs the others the sign is decided anyway.)
@@ -815,6 +818,15 @@ __global__ void __launch_bounds__(VO_MMA_LB) match_scan10_mma_kernel(
         // instructions per tile)
         (void)k_done;
         VO_COUNT(1, 1);
+        // Guard against data the filter cannot thin out (columns packed so tightly that a bf16 bound cannot separate
+        // them: every column of a tile survives for some row).  A tile in which one row keeps >= kDenseMinPerRow
+        // survivors is cheaper to evaluate outright - two columns per packed instruction, all rows together, the
+        // exact twin's arithmetic - than survivor by survivor; and the tiles that follow such a tile skip the filter
+        // altogether, re-probing every kDenseSkip tiles.  Exactness is unaffected: evaluating a column that the filter
+        // would have excluded can change neither value nor index (update_best_tie is order independent).
+        bool dense = dense_skip > 0;
+        if (dense) --dense_skip;
+        if (!dense)
 #pragma unroll
         for (int gq = 0; gq < 4; ++gq) {  // 4 column blocks = 32 columns = one mask word
           float run = FLT_MAX;
@@ -850,8 +862,40 @@ __global__ void __launch_bounds__(VO_MMA_LB) match_scan10_mma_kernel(
         const uint4 mk = *reinterpret_cast<const uint4*>(mask + lane * 4);
         const bool mine = (mk.x | mk.y | mk.z | mk.w) != 0;
         if (kFragBufs == 1 && k >= 0) fetch(k, 0);  // (the __syncwarp above: all lanes are done with the buffer)
-        if (!__any_sync(0xffffffffu, mine)) continue;
-        if (mine) {
+        if (!dense) {
+          if (!__any_sync(0xffffffffu, mine)) continue;
+          const int kept = __popc(mk.x) + __popc(mk.y) + __popc(mk.z) + __popc(mk.w);
+          if (__reduce_max_sync(0xffffffffu, kept) >= kDenseMinPerRow) {
+            dense = true;
+            dense_skip = kDenseSkip;
+            if (mine) *reinterpret_cast<uint4*>(mask + lane * 4) = make_uint4(0, 0, 0, 0);
+          }
+        }
+        if (dense) {
+          VO_COUNT(3, 1);
+          const long long j0 = t * kTileRows;
+          const int cnt = (int)((n2 - j0 < kTileRows) ? (n2 - j0) : kTileRows);
+          const int n_pairs = (cnt + 1) >> 1;
+          const float4* src = reinterpret_cast<const float4*>(rec + (j0 >> 1) * kPairFloats);
+          auto bc = [](float x) { return pack2(x, x); };
+          for (int p = 0; p < n_pairs; ++p) {
+            const float4 v0 = __ldg(src + 5 * p), v1 = __ldg(src + 5 * p + 1), v2 = __ldg(src + 5 * p + 2);
+            const float4 v3 = __ldg(src + 5 * p + 3), v4 = __ldg(src + 5 * p + 4);
+            const f2 x0 = sq2(pack2(v0.x, v0.y), bc(a[0])), x4 = sq2(pack2(v0.z, v0.w), bc(a[1]));
+            const f2 x2 = sq2(pack2(v1.x, v1.y), bc(a[2])), x6 = sq2(pack2(v1.z, v1.w), bc(a[3]));
+            const f2 x1 = sq2(pack2(v2.x, v2.y), bc(a[4])), x5 = sq2(pack2(v2.z, v2.w), bc(a[5]));
+            const f2 x3 = sq2(pack2(v3.x, v3.y), bc(a[6])), x7 = sq2(pack2(v3.z, v3.w), bc(a[7]));
+            const f2 x8 = sq2(pack2(v4.x, v4.y), bc(a[8])), x9 = sq2(pack2(v4.z, v4.w), bc(a[9]));
+            f2 d = add2(add2(add2(x0, x4), add2(x2, x6)), add2(add2(x1, x5), add2(x3, x7)));
+            d = add2(add2(d, x8), x9);
+            float d0, d1;
+            unpack2(d, d0, d1);
+            if (!__any_sync(0xffffffffu, (d0 <= bound) || (d1 <= bound))) continue;
+            if (d0 <= bound) update_best_tie(d0, __ldg(orig + j0 + 2 * p), best, second, idx);
+            if (2 * p + 1 < cnt && d1 <= bound) update_best_tie(d1, __ldg(orig + j0 + 2 * p + 1), best, second, idx);
+            bound = fminf(bound, second);
+          }
+        } else if (mine) {
           *reinterpret_cast<uint4*>(mask + lane * 4) = make_uint4(0, 0, 0, 0);
           auto survivors = [&](unsigned bits, int w) {
             while (bits) {
@@ -1054,13 +1098,13 @@ __global__ void idjoin_probe_kernel(const int* __restrict__ idA, long long row_b
 
 template <int DIM>
 void launch_scan(dim3 grid, cudaStream_t st, const float* A, long long rb, long long re, const float* B,
-                 long long n2, long long split, const unsigned* order, float* ob, float* os, int* oi) {
-  if (DIM == 10) match_scan10_kernel<<<grid, kMatchThreads, 0, st>>>(A, rb, re, B, n2, split, order, ob, os, oi);
+                 long long n2, long long split, const unsigned* order, float* ob, float* os, int* oi, bool plain) {
+  if (DIM == 10 && !plain) match_scan10_kernel<<<grid, kMatchThreads, 0, st>>>(A, rb, re, B, n2, split, order, ob, os, oi);
   else match_scan_kernel<DIM><<<grid, kMatchThreads, 0, st>>>(A, rb, re, B, n2, split, ob, os, oi);
 }
 
 typedef void (*scan_fn)(dim3, cudaStream_t, const float*, long long, long long, const float*, long long, long long,
-                        const unsigned*, float*, float*, int*);
+                        const unsigned*, float*, float*, int*, bool);
 
 constexpr long long kSortMinRows = 8192;  // below this the scan is latency-bound and the ordering does not pay
 constexpr long long kIndexMinRows = 8192;        // rows for which building the column index always pays (columns >= kSortMinRows)
@@ -1151,9 +1195,12 @@ int vo_match_dev(vo_ctx* ctx, const float* d_descA, int64_t n1, const float* d_d
   // too (tile boxes + tile skipping)
   // the column index costs ~0.4 ms per million columns to build: worth it for large row blocks and for small ones
   // against very many columns (measured, rows x 1M columns: 256 rows 0.96 vs 1.37 ms, 4096 rows 0.86 vs 11.4 ms)
-  const bool indexed = (dim == 10) && n2 >= kSortMinRows &&
+  // ctx->match_path (vo_match_set_path, diagnostics / bench): 1 = plain tiled brute force, 2 = Morton-ordered rows +
+  // exact packed scan, 3 = indexed walk with the exact fp32 scan of every visited tile, 0 / 4 = automatic
+  const int path = ctx->match_path;
+  const bool indexed = (dim == 10) && n2 >= kSortMinRows && path != VO_MATCH_PATH_BRUTE && path != VO_MATCH_PATH_ORDERED &&
                        (rows >= kIndexMinRows || (rows >= 32 && rows * n2 >= kIndexMinPairs));
-  const bool ordered = indexed || ((dim == 10) && rows >= kSortMinRows && n2 > 0);
+  const bool ordered = indexed || ((dim == 10) && rows >= kSortMinRows && n2 > 0 && path != VO_MATCH_PATH_BRUTE);
   if (indexed) n_splits = 1;
   size_t sort_tmp_bytes = 0;
   if (ordered) {
@@ -1243,7 +1290,8 @@ int vo_match_dev(vo_ctx* ctx, const float* d_descA, int64_t n1, const float* d_d
       while (n_warps < kMaxScanWarps && groups * n_warps * 2 <= (long long)ctx->sm_count * warp_budget) n_warps *= 2;
       // magnitudes the filter's error analysis does not cover select the exact scan (flag read on the device)
       int* range_flag = (int*)(base + o_small + 32);
-      static const bool force_exact = getenv("VO_MATCH_FORCE_EXACT") != nullptr;  // diagnostics: skip the filter
+      static const bool env_exact = getenv("VO_MATCH_FORCE_EXACT") != nullptr;  // diagnostics: skip the filter
+      const bool force_exact = env_exact || path == VO_MATCH_PATH_INDEXED_EXACT;
       if (force_exact) VO_CUDA(ctx, cudaMemsetAsync(range_flag, 1, 4, ctx->stream));
       match_range_check_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(d_descA + row_begin * 10, rows * 10, mm, range_flag);
       VO_CHECK_LAUNCH(ctx, "match_range_check_kernel");
@@ -1274,7 +1322,8 @@ int vo_match_dev(vo_ctx* ctx, const float* d_descA, int64_t n1, const float* d_d
   if (!indexed) {
     scan_fn scan = scan_for_dim(dim);
     dim3 grid((unsigned)row_blocks, (unsigned)n_splits);
-    scan(grid, ctx->stream, d_descA, row_begin, row_end, d_descB, n2, split_size, order, pb, ps, pi);
+    scan(grid, ctx->stream, d_descA, row_begin, row_end, d_descB, n2, split_size, order, pb, ps, pi,
+         path == VO_MATCH_PATH_BRUTE);
     VO_CHECK_LAUNCH(ctx, "match_scan_kernel");
   }
   match_merge_kernel<<<(unsigned)merge_blocks, 256, 0, ctx->stream>>>(pb, ps, pi, rows, (int)n_splits, dist_thr,
@@ -1307,6 +1356,12 @@ int vo_match_dev(vo_ctx* ctx, const float* d_descA, int64_t n1, const float* d_d
     stats[0] = (int64_t)((unsigned long long*)h)[2];
   }
   if (total > capacity) return vo_set_error(ctx, VO_ERR_CAPACITY, "vo_match", "pairs_out capacity");
+  return VO_OK;
+}
+
+int vo_match_set_path(vo_ctx* ctx, int path) {
+  if (!ctx || path < VO_MATCH_PATH_AUTO || path > VO_MATCH_PATH_INDEXED_FILTERED) return VO_ERR_INVALID;
+  ctx->match_path = path;
   return VO_OK;
 }
 

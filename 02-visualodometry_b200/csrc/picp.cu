@@ -63,7 +63,8 @@ struct PicpDev {
   unsigned int ticket;
   int round;      // rounds executed since the last reset
   int stop;       // set by the device-side convergence test
-  int bad_index;  // set by the pack kernel when a correspondence is out of range
+  int bad_index;  // set by the pack / gather / check kernels when a correspondence index is out of range
+  int timeout;    // set by the resident kernel when a wait for another CTA / GPU expired
   float prev_chi;
   float rel_tol;  // < 0: no convergence test
   vo_picp_stats stats[VO_PICP_MAX_ROUNDS];
@@ -107,6 +108,16 @@ __device__ __forceinline__ f2 neg2(f2 a) { return a ^ 0x8000000080000000ull; }
 // a*b rounded once and never contracted into a following add (see the note in picp_pair)
 __device__ __forceinline__ f2 prod2(f2 a, f2 b) { return fma2(a, b, 0ull); }
 
+// 1/z of two lanes: rcp.approx + one Newton step on FMA.  For 1e-30 <= z <= 1e30 this IS the correctly rounded
+// reciprocal (the sequence __frcp_rn runs after its range check); vo_selftest_reciprocal checks all 2^32 inputs.
+__device__ __forceinline__ f2 rcp2_newton(f2 z, float z0, float z1) {
+  float r0, r1;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(z0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(z1));
+  const f2 r = pack2(r0, r1);
+  return fma2(r, fma2(z, pack2(-r0, -r1), pack2(1.f, 1.f)), r);
+}
+
 // Two correspondences: exact part per point, then J, H += lambda J^T J and b += lambda J^T e in packed
 // f32x2 (lane 0 = first point, lane 1 = second; acc2[k] holds the two lanes' partial sums of slot k).
 // Points that do not contribute get all-zero Jacobian rows instead of a branch.
@@ -133,11 +144,7 @@ __device__ __forceinline__ void pair_front(const PicpCam& cam, const float* __re
   if (PINHOLE) {  // shortcut values for both lanes (see picp_project<> for why they are exact)
     s.q0 = add2(prod2(bc(cam.K[0]), s.c0), prod2(bc(cam.K[2]), s.c2));
     s.q1 = add2(prod2(bc(cam.K[4]), s.c1), prod2(bc(cam.K[5]), s.c2));
-    float r0, r1;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(s.t0.c2));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(s.t1.c2));
-    const f2 r = pack2(r0, r1);
-    s.iz = fma2(r, fma2(s.c2, pack2(-r0, -r1), bc(1.f)), r);
+    s.iz = rcp2_newton(s.c2, s.t0.c2, s.t1.c2);
   }
   unpack2(s.q0, s.t0.q0, s.t1.q0);
   unpack2(s.q1, s.t0.q1, s.t1.q1);
@@ -542,6 +549,292 @@ __global__ void __launch_bounds__(kLinThreads, kCtasPerSm) picp_linearize_kernel
   }
 }
 
+// ------------------------------------------------------------------ resident multi-round kernel
+// A correspondence set that fits the shared memory of the machine (148 SMs x 2816 quads = 1.67 M correspondences:
+// BASELINE config 2's 1 M frame, config 3's 10 M frame sharded over 8 GPUs, every frame of the bundled dataset) is
+// gathered ONCE into shared memory (28 B per correspondence read from HBM, nothing written back) and stays there for
+// all Gauss-Newton rounds of the frame: one cooperative launch, rounds 2..n touch neither HBM nor the launch path.
+// Per round and CTA: linearize the resident quads (same device functions, same rounding as the streaming kernel)
+// -> warp recursive-halving reduction -> CTA partial -> ONE exchange between the CTAs: every CTA publishes its 32
+// sums as self-validating 8-byte words {float bits | round sequence number} (payload and flag in one store: no
+// fence, no separate barrier) and every CTA polls all partials out of L2, adds them in CTA order in float64 and
+// solves the 6x6 system itself.  All CTAs add the same numbers in the same order, so they all hold the
+// bit-identical new pose without a broadcast and without a second grid-wide synchronisation.  With peers attached
+// only CTA 0 collects the GPU's partials; it pushes the GPU's 32 sums into every rank's mailbox over NVLink
+// (picp_peer_allreduce's protocol) and the warp 0 of EVERY CTA on every GPU polls its GPU's mailbox and adds the
+// ranks' sums in rank order.  Word buffers are double-buffered by round parity (a CTA can reach round r+2 only
+// after every CTA has published r+1, i.e. finished reading round r).  The convergence test of
+// exec/icp_test.cpp:99-106 runs inside the kernel: every CTA takes the same decision from the same sums.
+#ifndef VO_RES_THREADS
+#define VO_RES_THREADS 384
+#endif
+constexpr int kResThreads = VO_RES_THREADS;
+constexpr int kResWarps = kResThreads / 32;
+constexpr int kResMaxGrid = 160;   // CTAs whose partials one CTA can collect (B200: 148 SMs)
+constexpr int kResBatch = (kResMaxGrid + kResWarps - 1) / kResWarps;  // L2 loads in flight per polling thread
+constexpr int kResMaxQuads = 2816;  // quads per CTA: 5 planes x 2816 x 16 B = 225,280 B of the 232,448 B a CTA can own
+constexpr long long kResSpinLimit = 1ll << 21;  // ~2 s of polling: flag a timeout instead of hanging the GPU
+
+struct ResArgs {
+  const int2* pairs;
+  long long n;
+  const float* world;
+  long long n_world;
+  const float* image;
+  long long n_image;
+  PicpCam cam;
+  float thr, damping, rel_tol;
+  int n_rounds;
+  int quads_per_cta;
+  PicpDev* dev;
+  unsigned long long* ll;  // [2 parities][ll_stride CTAs][32 terms]
+  unsigned ll_seq0;        // round r of this launch carries sequence number ll_seq0 + 1 + r
+  int ll_stride;
+  int peer_n, peer_rank;
+  VoMailbox* peers[VO_MAX_PEERS];
+};
+
+__device__ __forceinline__ unsigned long long ld_poll(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st_poll(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+template <bool KEEP, bool PINHOLE>
+__global__ void __launch_bounds__(kResThreads, 1) picp_resident_kernel(const ResArgs a) {
+  extern __shared__ __align__(16) float4 s_pl[];  // [5 planes][quads_per_cta]: wx wy wz zu zv of 4 correspondences
+  __shared__ float s_part[kResWarps][kSlots];
+  __shared__ double s_fin[kResWarps][kSlots];
+  __shared__ double s_tot[kSlots];
+  __shared__ float s_pose[12];
+  __shared__ float s_dx[6];
+  __shared__ int s_stop;  // 0 go on, 1 converged, 2 a wait timed out
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int qpc = a.quads_per_cta;
+  const long long n_quads = (a.n + 3) >> 2;
+  const long long qb = (long long)blockIdx.x * qpc;
+  const long long qe = (qb + qpc < n_quads) ? qb + qpc : n_quads;
+  const int nq = qe > qb ? (int)(qe - qb) : 0;
+  const bool multi_cta = gridDim.x > 1;
+  const bool peers = a.peer_n > 1;
+  const bool collect = multi_cta && (!peers || blockIdx.x == 0);  // this CTA adds up the GPU's partials
+
+  // ---- gather once: (first: image index, second: world index) -> the CTA's planes in shared memory
+  {
+    bool bad = false;
+    for (int l = tid; l < nq; l += kResThreads) {
+      const long long i0 = (qb + l) * 4;
+      float wx[4], wy[4], wz[4], zu[4], zv[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        wx[k] = wy[k] = wz[k] = zu[k] = zv[k] = 0.f;  // padding lanes of the last quad: finite, masked by `left`
+        if (i0 + k < a.n) {
+          const int2 pr = __ldg(a.pairs + i0 + k);
+          if (pr.x < 0 || pr.x >= a.n_image || pr.y < 0 || pr.y >= a.n_world) {
+            bad = true;
+            wz[k] = -1.f;
+          } else {
+            const float* w = a.world + 3ll * pr.y;
+            const float2 z = __ldg(reinterpret_cast<const float2*>(a.image) + pr.x);
+            wx[k] = __ldg(w);
+            wy[k] = __ldg(w + 1);
+            wz[k] = __ldg(w + 2);
+            zu[k] = z.x;
+            zv[k] = z.y;
+          }
+        }
+      }
+      s_pl[l] = make_float4(wx[0], wx[1], wx[2], wx[3]);
+      s_pl[qpc + l] = make_float4(wy[0], wy[1], wy[2], wy[3]);
+      s_pl[2 * qpc + l] = make_float4(wz[0], wz[1], wz[2], wz[3]);
+      s_pl[3 * qpc + l] = make_float4(zu[0], zu[1], zu[2], zu[3]);
+      s_pl[4 * qpc + l] = make_float4(zv[0], zv[1], zv[2], zv[3]);
+    }
+    if (bad) a.dev->bad_index = 1;
+  }
+  if (tid < 12) s_pose[tid] = a.dev->pose[tid];
+  if (tid == 0) s_stop = 0;
+  VoMailbox* me = peers ? a.peers[a.peer_rank] : nullptr;
+  const unsigned mb_seq0 = peers ? *(volatile unsigned*)&me->seq : 0u;
+  float prev_chi = FLT_MAX;  // (lane 0 of warp 0)
+  __syncthreads();
+
+  int r = 0;
+  for (; r < a.n_rounds; ++r) {
+    float T[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) T[i] = s_pose[i];
+    f2 acc2[29];
+#pragma unroll
+    for (int i = 0; i < 29; ++i) acc2[i] = 0ull;
+    int n_in = 0, n_out = 0;
+    for (int l = tid; l < nq; l += kResThreads) {
+      const float4 wx = s_pl[l], wy = s_pl[qpc + l], wz = s_pl[2 * qpc + l], zu = s_pl[3 * qpc + l], zv = s_pl[4 * qpc + l];
+      const long long left = a.n - (qb + l) * 4;  // >= 1; < 4 only in the last quad of the set
+      int s0, s1, s2, s3;
+      PairState pa, pb;
+      pair_front<PINHOLE>(a.cam, T, wx.x, wy.x, wz.x, wx.y, wy.y, wz.y, pa);
+      pair_front<PINHOLE>(a.cam, T, wx.z, wy.z, wz.z, wx.w, wy.w, wz.w, pb);
+      if (pa.fix0 || pa.fix1 || pb.fix0 || pb.fix1) {
+        pair_fix(a.cam, pa);
+        pair_fix(a.cam, pb);
+      }
+      pair_back<KEEP, PINHOLE>(a.cam, a.thr, pa, zu.x, zv.x, zu.y, zv.y, true, left > 1, acc2, n_in, n_out, s0, s1);
+      pair_back<KEEP, PINHOLE>(a.cam, a.thr, pb, zu.z, zv.z, zu.w, zv.w, left > 2, left > 3, acc2, n_in, n_out, s2, s3);
+    }
+    // ---- warp reduction: lane L ends up with the warp's total of term L (counts are exact in float: < 2^24)
+    {
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 29; ++i) {
+        float lo, hi;
+        unpack2(acc2[i], lo, hi);
+        v[i] = lo + hi;
+      }
+      v[29] = (float)n_in;
+      v[30] = (float)n_out;
+      v[31] = 0.f;
+      s_part[warp][lane] = warp_sum32_scatter(v, lane);
+    }
+    __syncthreads();
+    const unsigned seq = a.ll_seq0 + 1u + (unsigned)r;
+    bool timed_out = false;
+    if (multi_cta) {
+      unsigned long long* buf = a.ll + (size_t)(seq & 1u) * a.ll_stride * kSlots;
+      if (warp == 0) {  // publish this CTA's partial: term `lane`, warps added in warp order
+        float p = 0.f;
+#pragma unroll
+        for (int w = 0; w < kResWarps; ++w) p += s_part[w][lane];
+        st_poll(buf + (size_t)blockIdx.x * kSlots + lane, (unsigned long long)__float_as_uint(p) | ((unsigned long long)seq << 32));
+      }
+      if (collect) {  // thread (warp, lane): term `lane` of CTAs warp, warp + kResWarps, ... all loads in flight at once
+        unsigned long long w[kResBatch];
+        long long spins = 0;
+        for (;;) {
+          bool ok = true;
+#pragma unroll
+          for (int u = 0; u < kResBatch; ++u) {
+            const unsigned b = warp + u * kResWarps;
+            w[u] = (b < gridDim.x) ? ld_poll(buf + (size_t)b * kSlots + lane) : ((unsigned long long)seq << 32);
+          }
+#pragma unroll
+          for (int u = 0; u < kResBatch; ++u) ok = ok && ((unsigned)(w[u] >> 32) == seq);
+          if (ok) break;
+          if (++spins > kResSpinLimit) {
+            timed_out = true;
+            break;
+          }
+        }
+        double v = 0.0;
+#pragma unroll
+        for (int u = 0; u < kResBatch; ++u) {
+          const unsigned b = warp + u * kResWarps;
+          if (b < gridDim.x) v += (double)__uint_as_float((unsigned)w[u]);
+        }
+        s_fin[warp][lane] = v;
+      }
+    }
+    if (__syncthreads_or(timed_out)) {
+      if (tid == 0) a.dev->timeout = 1;
+      if (tid == 0) s_stop = 2;
+      __syncthreads();
+      break;
+    }
+    if (warp == 0) {
+      double tot = 0.0;
+      if (collect) {
+#pragma unroll
+        for (int w = 0; w < kResWarps; ++w) tot += s_fin[w][lane];
+      } else if (!multi_cta) {
+#pragma unroll
+        for (int w = 0; w < kResWarps; ++w) tot += (double)s_part[w][lane];
+      }
+      bool ok = true;
+      if (peers) {
+        const unsigned mseq = mb_seq0 + 1u + (unsigned)r;
+        const int par = (int)(mseq & 1u);
+        if (blockIdx.x == 0) {  // the GPU's sums -> every rank's mailbox (mine included), 8-byte self-validating words
+          const unsigned long long bits = (unsigned long long)__double_as_longlong(tot), tag = (unsigned long long)mseq << 32;
+          const unsigned long long w0 = (bits & 0xffffffffull) | tag, w1 = (bits >> 32) | tag;
+          for (int p = 0; p < a.peer_n; ++p) {
+            volatile unsigned long long* dst = &a.peers[p]->ll[par][a.peer_rank][lane][0];
+            dst[0] = w0;
+            dst[1] = w1;
+          }
+        }
+        // every CTA: term `lane` of every rank out of this GPU's mailbox, added in RANK order
+        tot = 0.0;
+        for (int q = 0; q < a.peer_n; ++q) {
+          const volatile unsigned long long* src = &me->ll[par][q][lane][0];
+          unsigned long long r0 = src[0], r1 = src[1];
+          long long spins = 0;
+          while ((unsigned)(r0 >> 32) != mseq || (unsigned)(r1 >> 32) != mseq) {
+            if (++spins > (1ll << 23)) {
+              ok = false;
+              break;
+            }
+            r0 = src[0];
+            r1 = src[1];
+          }
+          tot += __longlong_as_double((long long)((r0 & 0xffffffffull) | (r1 << 32)));
+        }
+        ok = __all_sync(0xffffffffu, ok);
+      }
+      s_tot[lane] = tot;
+      __syncwarp();
+      if (lane == 0) {
+        float Hu[21], bb[6];
+#pragma unroll
+        for (int k = 0; k < 21; ++k) Hu[k] = (float)s_tot[k];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) bb[k] = (float)s_tot[21 + k];
+        float dx[6];
+        picp_gn_solve(Hu, bb, a.damping, dx);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) s_dx[k] = dx[k];
+        vo_picp_stats st;
+        st.chi_inliers = (float)s_tot[27];
+        st.chi_outliers = (float)s_tot[28];
+        st.num_inliers = (int)s_tot[29];
+        st.num_outliers = (int)s_tot[30];
+        if (blockIdx.x == 0 && r < VO_PICP_MAX_ROUNDS) a.dev->stats[r] = st;
+        int stop = 0;
+        if (a.rel_tol >= 0.f) {  // exec/icp_test.cpp:99-106
+          const float cur = st.chi_inliers;
+          const float rel = (prev_chi > 1e-10f) ? __fdiv_rn(fabsf(__fsub_rn(prev_chi, cur)), prev_chi) : 0.f;
+          if (rel < a.rel_tol) stop = 1;
+          prev_chi = cur;
+        }
+        if (!ok) {
+          stop = 2;
+          me->timeout = 1u;
+        }
+        s_stop = stop;
+      }
+      __syncwarp();
+      picp_apply_dx_warp(s_dx, s_pose, lane);
+    }
+    __syncthreads();
+    if (s_stop) {
+      ++r;
+      break;
+    }
+  }
+  if (blockIdx.x == 0) {
+    if (tid < 12) a.dev->pose[tid] = s_pose[tid];
+    if (tid == 0) {
+      a.dev->round = r;
+      a.dev->stop = (s_stop == 1);
+      a.dev->prev_chi = prev_chi;
+      a.dev->rel_tol = a.rel_tol;
+      if (peers) *(volatile unsigned*)&me->seq = mb_seq0 + (unsigned)r;
+    }
+  }
+}
+
 // multi-GPU tail: after the all-reduce every rank runs the identical solve
 __global__ void picp_solve_kernel(const double* result, float damping, PicpDev* dev) {
   if (threadIdx.x == 0 && !dev->stop) picp_solve_update(result, damping, dev);
@@ -575,6 +868,46 @@ __global__ void __launch_bounds__(256) picp_pack_kernel(const int2* __restrict__
   pk[4 * stride + i] = z.y;
 }
 
+// range check of a correspondence set without packing it (host-buffer entry point; the planes are built lazily)
+__global__ void __launch_bounds__(256) picp_check_kernel(const int2* __restrict__ pairs, long long n, long long n_world,
+                                                         long long n_image, PicpDev* dev) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int2 pr = __ldg(pairs + i);
+  if (pr.x < 0 || pr.x >= n_image || pr.y < 0 || pr.y >= n_world) dev->bad_index = 1;
+}
+
+// exhaustive check of the reciprocal shortcut: every float bit pattern inside the gate of pair_front / picp_project
+// against __frcp_rn and IEEE 1.f / z.  out: [0] inputs inside the gate, [1] mismatches of the packed form,
+// [2] mismatches of the scalar form (vo_device.cuh picp_project), [3] first mismatching input + 1
+__global__ void __launch_bounds__(256) picp_rcp_selftest_kernel(unsigned long long* out) {
+  unsigned long long in_gate = 0, bad_packed = 0, bad_scalar = 0;
+  const unsigned long long total = 1ull << 32, step = (unsigned long long)gridDim.x * blockDim.x * 2;
+  for (unsigned long long i = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) * 2; i < total; i += step) {
+    const float z0 = __uint_as_float((unsigned)i), z1 = __uint_as_float((unsigned)(i + 1));
+    float p0, p1;
+    unpack2(rcp2_newton(pack2(z0, z1), z0, z1), p0, p1);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const float z = k ? z1 : z0, p = k ? p1 : p0;
+      if (!((z >= 1e-30f) && (z <= 1e30f))) continue;
+      ++in_gate;
+      const float ref = __frcp_rn(z), ref2 = __fdiv_rn(1.f, z);
+      float r;
+      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(z));
+      const float sc = fmaf(r, fmaf(-z, r, 1.f), r);
+      const bool bp = __float_as_uint(p) != __float_as_uint(ref) || __float_as_uint(ref) != __float_as_uint(ref2);
+      const bool bs = __float_as_uint(sc) != __float_as_uint(ref);
+      bad_packed += bp;
+      bad_scalar += bs;
+      if (bp || bs) atomicMin(out + 3, (unsigned long long)__float_as_uint(z) + 1ull);
+    }
+  }
+  atomicAdd(out + 0, in_gate);
+  if (bad_packed) atomicAdd(out + 1, bad_packed);
+  if (bad_scalar) atomicAdd(out + 2, bad_scalar);
+}
+
 struct PoseArg { float p[12]; };
 // the pose travels as a kernel argument: no staging buffer, no host synchronisation
 __global__ void picp_set_pose_kernel(PicpDev* dev, PoseArg pose) {
@@ -604,6 +937,11 @@ cudaError_t lin_opt_in_all() {
   if (e == cudaSuccess) e = lin_opt_in<true, false, true>();
   if (e == cudaSuccess) e = lin_opt_in<true, true, false>();
   if (e == cudaSuccess) e = lin_opt_in<true, true, true>();
+  const int res_smem = (int)(kResMaxQuads * 5 * sizeof(float4));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(picp_resident_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, res_smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(picp_resident_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, res_smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(picp_resident_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, res_smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(picp_resident_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, res_smem);
   return e;
 }
 
@@ -634,6 +972,11 @@ struct vo_picp {
   PicpDev* d_dev = nullptr;
   int max_grid = 0;
   int last_rounds = 0;
+  const int32_t* d_pairs_cur = nullptr;  // the current correspondence set (borrowed, or d_pairs)
+  bool packed = false;                   // d_pk holds the planes of the current set
+  unsigned long long* d_ll = nullptr;    // resident kernel: [2][kResMaxGrid][32] self-validating words
+  unsigned ll_seq = 0;                   // sequence number of the last round exchanged through d_ll
+  int mode = VO_PICP_MODE_AUTO;
 };
 
 namespace {
@@ -679,8 +1022,27 @@ void launch_lin2(bool pinhole, int grid, cudaStream_t st, const LinArgs& a, bool
   else launch_lin3<KEEP, STATUS, false>(grid, st, a, pdl);
 }
 
+// the streaming kernel reads the packed planes: build them on first use (picp_pack_kernel, once per set)
+int ensure_packed(vo_picp* s) {
+  if (s->packed) return VO_OK;
+  vo_ctx* ctx = s->ctx;
+  int st = grow(ctx, (void**)&s->d_pk, &s->pk_cap, (size_t)s->n_pad * 5 * sizeof(float));
+  if (st) return st;
+  if (s->n_pairs) {
+    const long long blocks = (s->n_pad + 255) / 256;
+    picp_pack_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(reinterpret_cast<const int2*>(s->d_pairs_cur), s->n_pairs,
+                                                               s->d_world, s->n_world, s->d_image, s->n_image,
+                                                               s->d_pk, s->n_pad, s->d_dev);
+    VO_CHECK_LAUNCH(ctx, "picp_pack_kernel");
+  }
+  s->packed = true;
+  return VO_OK;
+}
+
 int launch_linearize(vo_picp* s, float thr, float damping, bool keep, bool status, bool fuse_solve) {
   vo_ctx* ctx = s->ctx;
+  int st = ensure_packed(s);
+  if (st) return st;
   LinArgs a;
   a.pk = s->d_pk;
   a.n = s->n_pairs;
@@ -707,6 +1069,80 @@ int launch_linearize(vo_picp* s, float thr, float damping, bool keep, bool statu
     else launch_lin2<false, false>(s->pinhole, grid, ctx->stream, a, pdl);
   }
   VO_CHECK_LAUNCH(ctx, "picp_linearize_kernel");
+  return VO_OK;
+}
+
+// ---- resident path: geometry of the launch, or grid = 0 when the set does not fit / the mode forbids it
+struct ResPlan { int grid, quads_per_cta; size_t smem; };
+
+ResPlan resident_plan(const vo_picp* s, int n_rounds) {
+  ResPlan p = {0, 0, 0};
+  const vo_ctx* ctx = s->ctx;
+  if (s->mode == VO_PICP_MODE_STREAM) return p;
+  if (ctx->nccl_comm != nullptr && ctx->peer_n <= 1) return p;  // NCCL-only exchange happens between launches
+  if (s->mode == VO_PICP_MODE_AUTO && n_rounds < 2 && s->packed) return p;  // one round of a packed set: stream 20 B
+  const long long n_quads = (s->n_pairs + 3) / 4;
+  int max_grid = s->max_grid < kResMaxGrid ? s->max_grid : kResMaxGrid;
+  long long g = (n_quads + kResThreads - 1) / kResThreads;  // at least one quad per thread and round
+  if (g < 1) g = 1;
+  if (g > max_grid) g = max_grid;
+  long long qpc = (n_quads + g - 1) / g;
+  if (qpc < 1) qpc = 1;
+  if (qpc > kResMaxQuads) return p;
+  p.grid = (int)g;
+  p.quads_per_cta = (int)qpc;
+  p.smem = (size_t)qpc * 5 * sizeof(float4);
+  return p;
+}
+
+template <bool KEEP, bool PINHOLE>
+cudaError_t launch_res2(const ResPlan& pl, cudaStream_t st, const ResArgs& a) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)pl.grid);
+  cfg.blockDim = dim3(kResThreads);
+  cfg.dynamicSmemBytes = pl.smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;  // all CTAs co-resident: they wait for each other's partials
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pl.grid > 1 ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, picp_resident_kernel<KEEP, PINHOLE>, a);
+}
+
+// n_rounds Gauss-Newton rounds (fewer if rel_tol >= 0 and the driver's test converges) in ONE launch
+int launch_resident(vo_picp* s, const ResPlan& pl, float thr, float damping, bool keep, int n_rounds, float rel_tol) {
+  vo_ctx* ctx = s->ctx;
+  if (s->ll_seq > 0xF0000000u) {  // sequence numbers about to wrap: start over from clean words
+    VO_CUDA(ctx, cudaMemsetAsync(s->d_ll, 0, sizeof(unsigned long long) * 2 * kResMaxGrid * kSlots, ctx->stream));
+    s->ll_seq = 0;
+  }
+  ResArgs a;
+  a.pairs = reinterpret_cast<const int2*>(s->d_pairs_cur);
+  a.n = s->n_pairs;
+  a.world = s->d_world;
+  a.n_world = s->n_world;
+  a.image = s->d_image;
+  a.n_image = s->n_image;
+  a.cam = s->cam;
+  a.thr = thr;
+  a.damping = damping;
+  a.rel_tol = rel_tol;
+  a.n_rounds = n_rounds;
+  a.quads_per_cta = pl.quads_per_cta;
+  a.dev = s->d_dev;
+  a.ll = s->d_ll;
+  a.ll_seq0 = s->ll_seq;
+  a.ll_stride = kResMaxGrid;
+  a.peer_n = ctx->peer_n > 1 ? ctx->peer_n : 0;
+  a.peer_rank = ctx->peer_rank;
+  for (int p = 0; p < VO_MAX_PEERS; ++p) a.peers[p] = (VoMailbox*)ctx->peer_mailbox[p];
+  s->ll_seq += (unsigned)n_rounds;
+  cudaError_t e;
+  if (keep) e = s->pinhole ? launch_res2<true, true>(pl, ctx->stream, a) : launch_res2<true, false>(pl, ctx->stream, a);
+  else e = s->pinhole ? launch_res2<false, true>(pl, ctx->stream, a) : launch_res2<false, false>(pl, ctx->stream, a);
+  ctx->launches++;
+  if (e != cudaSuccess) return vo_set_error(ctx, VO_ERR_CUDA, "picp_resident_kernel", cudaGetErrorString(e));
   return VO_OK;
 }
 
@@ -757,6 +1193,9 @@ int vo_picp_create(vo_ctx* ctx, vo_picp** out) {
   if (e == cudaSuccess) e = cudaMalloc((void**)&s->d_result, kSlots * sizeof(double));
   if (e == cudaSuccess) e = cudaMalloc((void**)&s->d_dev, sizeof(PicpDev));
   if (e == cudaSuccess) e = cudaMemsetAsync(s->d_dev, 0, sizeof(PicpDev), ctx->stream);
+  const size_t ll_bytes = sizeof(unsigned long long) * 2 * kResMaxGrid * kSlots;
+  if (e == cudaSuccess) e = cudaMalloc((void**)&s->d_ll, ll_bytes);
+  if (e == cudaSuccess) e = cudaMemsetAsync(s->d_ll, 0, ll_bytes, ctx->stream);
   if (e != cudaSuccess) {
     vo_set_error(ctx, VO_ERR_CUDA, "vo_picp_create", cudaGetErrorString(e));
     vo_picp_destroy(s);
@@ -785,6 +1224,7 @@ int vo_picp_destroy(vo_picp* s) {
   if (s->d_partials) cudaFree(s->d_partials);
   if (s->d_result) cudaFree(s->d_result);
   if (s->d_dev) cudaFree(s->d_dev);
+  if (s->d_ll) cudaFree(s->d_ll);
   delete s;
   return VO_OK;
 }
@@ -844,14 +1284,17 @@ int vo_picp_set_points(vo_picp* s, const float* world_xyz, int64_t n_world, cons
   s->n_world = n_world;
   s->n_image = n_image;
   s->n_pairs = -1;
+  s->packed = false;
   return VO_OK;
 }
 
 int vo_picp_set_points_dev(vo_picp* s, const float* d_world_xyz, int64_t n_world, const float* d_image_xy,
                            int64_t n_image) {
   if (!s || n_world < 0 || n_image < 0 || !d_world_xyz || !d_image_xy) return VO_ERR_INVALID;
+  int st = vo_ctx_activate(s->ctx);  // the frees below must run on this context's device
+  if (st) return st;
   if (s->own_points) {
-    cudaStreamSynchronize(s->ctx->stream);
+    VO_CUDA(s->ctx, cudaStreamSynchronize(s->ctx->stream));
     if (s->d_world) cudaFree(s->d_world);
     if (s->d_image) cudaFree(s->d_image);
     s->world_cap = s->image_cap = 0;
@@ -862,6 +1305,7 @@ int vo_picp_set_points_dev(vo_picp* s, const float* d_world_xyz, int64_t n_world
   s->n_world = n_world;
   s->n_image = n_image;
   s->n_pairs = -1;
+  s->packed = false;
   return VO_OK;
 }
 
@@ -871,18 +1315,15 @@ int vo_picp_set_correspondences_dev(vo_picp* s, const int32_t* d_pairs, int64_t 
   if (!s->d_world || !s->d_image) return vo_set_error(ctx, VO_ERR_STATE, "picp", "set_points not called");
   int st = vo_ctx_activate(ctx);
   if (st) return st;
+  // Nothing is gathered here: the resident kernel gathers straight into shared memory, the streaming kernel
+  // packs its planes on first use (ensure_packed).  d_pairs stays borrowed until the next set_correspondences*.
   const long long n_pad = (n_pairs + 3) / 4 * 4;
-  st = grow(ctx, (void**)&s->d_pk, &s->pk_cap, (size_t)(n_pad > 0 ? n_pad : 4) * 5 * sizeof(float));
-  if (st) return st;
   s->n_pad = n_pad > 0 ? n_pad : 4;
   s->n_pairs = n_pairs;
-  if (n_pairs) {
-    const long long blocks = (n_pad + 255) / 256;
-    picp_pack_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(reinterpret_cast<const int2*>(d_pairs), n_pairs,
-                                                               s->d_world, s->n_world, s->d_image, s->n_image,
-                                                               s->d_pk, s->n_pad, s->d_dev);
-    VO_CHECK_LAUNCH(ctx, "picp_pack_kernel");
-  }
+  s->d_pairs_cur = d_pairs;
+  s->packed = false;
+  // a fresh set starts with a clean range-check flag (the gather / pack / check kernels raise it)
+  VO_CUDA(ctx, cudaMemsetAsync(&s->d_dev->bad_index, 0, sizeof(int), ctx->stream));
   return VO_OK;
 }
 
@@ -896,7 +1337,13 @@ int vo_picp_set_correspondences(vo_picp* s, const int32_t* pairs, int64_t n_pair
   if (n_pairs) VO_CUDA(ctx, cudaMemcpyAsync(s->d_pairs, pairs, (size_t)n_pairs * 8, cudaMemcpyHostToDevice, ctx->stream));
   st = vo_picp_set_correspondences_dev(s, s->d_pairs, n_pairs);
   if (st) return st;
-  // range check result + the caller may release `pairs` after return
+  // synchronous contract of the host entry point: indices are range-checked before it returns, and the caller
+  // may release `pairs` afterwards
+  if (n_pairs) {
+    picp_check_kernel<<<(unsigned)((n_pairs + 255) / 256), 256, 0, ctx->stream>>>(
+        reinterpret_cast<const int2*>(s->d_pairs), n_pairs, s->n_world, s->n_image, s->d_dev);
+    VO_CHECK_LAUNCH(ctx, "picp_check_kernel");
+  }
   void* h;
   st = vo_pinned(ctx, 64, &h);
   if (st) return st;
@@ -907,6 +1354,64 @@ int vo_picp_set_correspondences(vo_picp* s, const int32_t* pairs, int64_t n_pair
     s->n_pairs = -1;
     return vo_set_error(ctx, VO_ERR_INVALID, "vo_picp_set_correspondences", "index out of range");
   }
+  return VO_OK;
+}
+
+int vo_selftest_reciprocal(vo_ctx* ctx, uint64_t out[4]) {
+  if (!ctx || !out) return VO_ERR_INVALID;
+  int st = vo_ctx_activate(ctx);
+  if (st) return st;
+  void* d;
+  st = vo_scratch(ctx, 64, &d);
+  if (st) return st;
+  const unsigned long long init[4] = {0, 0, 0, ~0ull};
+  VO_CUDA(ctx, cudaMemcpyAsync(d, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+  picp_rcp_selftest_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>((unsigned long long*)d);
+  VO_CHECK_LAUNCH(ctx, "picp_rcp_selftest_kernel");
+  unsigned long long h[4];
+  VO_CUDA(ctx, cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  VO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  out[0] = h[0];
+  out[1] = h[1];
+  out[2] = h[2];
+  out[3] = (h[3] == ~0ull) ? 0 : h[3];
+  return VO_OK;
+}
+
+int vo_picp_pack(vo_picp* s) {
+  int st = ready(s);
+  if (st) return st;
+  return ensure_packed(s);
+}
+
+int vo_picp_set_mode(vo_picp* s, int mode) {
+  if (!s || mode < VO_PICP_MODE_AUTO || mode > VO_PICP_MODE_RESIDENT) return VO_ERR_INVALID;
+  s->mode = mode;
+  return VO_OK;
+}
+
+int vo_picp_resident_capacity(const vo_picp* s, int64_t* n_pairs_max) {
+  if (!s || !n_pairs_max) return VO_ERR_INVALID;
+  const int g = s->max_grid < kResMaxGrid ? s->max_grid : kResMaxGrid;
+  *n_pairs_max = (int64_t)g * kResMaxQuads * 4;
+  return VO_OK;
+}
+
+// the sticky per-set flags of the device state: an out-of-range index on the _dev path, an expired wait
+static int check_dev_flags(vo_picp* s, const char* who) {
+  vo_ctx* ctx = s->ctx;
+  struct Flags { int bad_index, timeout; };
+  void* h;
+  int st = vo_pinned(ctx, 64, &h);
+  if (st) return st;
+  VO_CUDA(ctx, cudaMemcpyAsync(h, &s->d_dev->bad_index, sizeof(Flags), cudaMemcpyDeviceToHost, ctx->stream));
+  VO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  const Flags f = *(const Flags*)h;
+  if (f.timeout) {
+    VO_CUDA(ctx, cudaMemsetAsync(&s->d_dev->timeout, 0, sizeof(int), ctx->stream));
+    return vo_set_error(ctx, VO_ERR_STATE, who, "a wait inside the resident kernel timed out (CTAs / ranks out of step)");
+  }
+  if (f.bad_index) return vo_set_error(ctx, VO_ERR_INVALID, who, "correspondence index out of range");
   return VO_OK;
 }
 
@@ -954,13 +1459,17 @@ int vo_picp_enqueue_rounds(vo_picp* s, float thr, float damping, int keep_outlie
   int st = ready(s);
   if (st) return st;
   if (n_rounds < 0 || n_rounds > VO_PICP_MAX_ROUNDS) return vo_set_error(s->ctx, VO_ERR_INVALID, "vo_picp_enqueue_rounds", "n_rounds");
+  s->last_rounds = n_rounds;
+  const ResPlan pl = resident_plan(s, n_rounds);
+  if (pl.grid > 0) return n_rounds ? launch_resident(s, pl, thr, damping, keep_outliers != 0, n_rounds, -1.f) : VO_OK;
+  if (s->mode == VO_PICP_MODE_RESIDENT)
+    return vo_set_error(s->ctx, VO_ERR_CAPACITY, "vo_picp_enqueue_rounds", "VO_PICP_MODE_RESIDENT: the set does not fit shared memory");
   st = reset_rounds(s, -1.f);
   if (st) return st;
   for (int r = 0; r < n_rounds; ++r) {
     st = enqueue_round(s, thr, damping, keep_outliers != 0);
     if (st) return st;
   }
-  s->last_rounds = n_rounds;
   return VO_OK;
 }
 
@@ -978,6 +1487,8 @@ int vo_picp_fetch_stats(vo_picp* s, vo_picp_stats* stats_out, int n_rounds) {
     VO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (*(unsigned*)hp) return vo_set_error(ctx, VO_ERR_STATE, "vo_picp_fetch_stats", "peer exchange timed out (ranks out of step)");
   }
+  st = check_dev_flags(s, "vo_picp_fetch_stats");
+  if (st) return st;
   if (stats_out && n_rounds) {
     void* h;
     st = vo_pinned(ctx, sizeof(vo_picp_stats) * VO_PICP_MAX_ROUNDS, &h);
@@ -985,8 +1496,6 @@ int vo_picp_fetch_stats(vo_picp* s, vo_picp_stats* stats_out, int n_rounds) {
     VO_CUDA(ctx, cudaMemcpyAsync(h, s->d_dev->stats, sizeof(vo_picp_stats) * n_rounds, cudaMemcpyDeviceToHost, ctx->stream));
     VO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     memcpy(stats_out, h, sizeof(vo_picp_stats) * n_rounds);
-  } else {
-    VO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   }
   return VO_OK;
 }
@@ -1010,25 +1519,40 @@ int vo_picp_solve(vo_picp* s, float thr, float damping, int keep_outliers, int m
   if (st) return st;
   vo_ctx* ctx = s->ctx;
   if (max_rounds < 1 || max_rounds > VO_PICP_MAX_ROUNDS || rel_tol < 0.f) return vo_set_error(ctx, VO_ERR_INVALID, "vo_picp_solve", "max_rounds / rel_tol");
-  st = reset_rounds(s, rel_tol);
-  if (st) return st;
   struct Head { int round, stop; };
   void* h;
   st = vo_pinned(ctx, sizeof(vo_picp_stats) * VO_PICP_MAX_ROUNDS, &h);
   if (st) return st;
-  const int chunk = 8;  // rounds enqueued between host polls of the device-side stop flag
   int done = 0;
-  for (int r = 0; r < max_rounds;) {
-    const int m = (max_rounds - r < chunk) ? max_rounds - r : chunk;
-    for (int i = 0; i < m; ++i) {
-      st = enqueue_round(s, thr, damping, keep_outliers != 0);
-      if (st) return st;
-    }
-    r += m;
+  const ResPlan pl = resident_plan(s, max_rounds);
+  if (pl.grid > 0) {  // the whole driver loop in one launch: the convergence test runs inside the kernel
+    st = launch_resident(s, pl, thr, damping, keep_outliers != 0, max_rounds, rel_tol);
+    if (st) return st;
+    st = check_dev_flags(s, "vo_picp_solve");
+    if (st) return st;
     VO_CUDA(ctx, cudaMemcpyAsync(h, &s->d_dev->round, sizeof(Head), cudaMemcpyDeviceToHost, ctx->stream));
     VO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     done = ((Head*)h)->round;
-    if (((Head*)h)->stop) break;
+  } else {
+    if (s->mode == VO_PICP_MODE_RESIDENT)
+      return vo_set_error(ctx, VO_ERR_CAPACITY, "vo_picp_solve", "VO_PICP_MODE_RESIDENT: the set does not fit shared memory");
+    st = reset_rounds(s, rel_tol);
+    if (st) return st;
+    const int chunk = 8;  // rounds enqueued between host polls of the device-side stop flag
+    for (int r = 0; r < max_rounds;) {
+      const int m = (max_rounds - r < chunk) ? max_rounds - r : chunk;
+      for (int i = 0; i < m; ++i) {
+        st = enqueue_round(s, thr, damping, keep_outliers != 0);
+        if (st) return st;
+      }
+      r += m;
+      VO_CUDA(ctx, cudaMemcpyAsync(h, &s->d_dev->round, sizeof(Head), cudaMemcpyDeviceToHost, ctx->stream));
+      VO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      done = ((Head*)h)->round;
+      if (((Head*)h)->stop) break;
+    }
+    st = check_dev_flags(s, "vo_picp_solve");
+    if (st) return st;
   }
   if (rounds_done) *rounds_done = done;
   if (last && done > 0) {

@@ -36,6 +36,7 @@ struct vo_ctx {
   void* peer_mailbox[VO_MAX_PEERS] = {nullptr};
   int peer_n = 0;     // 0: not attached
   int peer_rank = 0;
+  int match_path = 0;  // VO_MATCH_PATH_*: which of the (all bit-exact) matcher paths vo_match takes
 };
 
 // mailbox layout: [2 parities][VO_MAX_PEERS ranks][32 terms] x two 8-byte words {32 payload bits | sequence number << 32}

@@ -124,7 +124,23 @@ int vo_picp_set_points_dev(vo_picp* s, const float* d_world_xyz, int64_t n_world
 /* correspondences (first: image index, second: world index), src/picp_solver.cpp:62-70.
  * Indices are range-checked on the device; out of range -> VO_ERR_INVALID. */
 int vo_picp_set_correspondences(vo_picp* s, const int32_t* pairs, int64_t n_pairs);
+/* d_pairs is BORROWED until the next set_correspondences* call (nothing is gathered at this point: the resident
+ * kernel gathers straight into shared memory, the streaming kernel packs its planes on first use). An index out
+ * of range is reported by the next vo_picp_fetch_stats / vo_picp_solve / vo_picp_linearize (VO_ERR_INVALID). */
 int vo_picp_set_correspondences_dev(vo_picp* s, const int32_t* d_pairs, int64_t n_pairs);
+/* Which kernel runs the Gauss-Newton rounds (diagnostic; results agree to float rounding, masks bit for bit):
+ * AUTO: a set that fits the machine's shared memory (vo_picp_resident_capacity, 1.67 M correspondences on a B200)
+ *       and is solved for >= 2 rounds per call runs in ONE persistent cooperative launch with the correspondences
+ *       resident in shared memory across all rounds; anything else streams the packed planes once per round.
+ * STREAM / RESIDENT force one of the two (RESIDENT fails with VO_ERR_CAPACITY when the set does not fit). */
+/* Builds the streaming kernel's packed planes of the current set now (picp_pack_kernel, 48 B per correspondence of
+ * traffic) instead of lazily inside the first streamed round; a no-op when they exist. */
+int vo_picp_pack(vo_picp* s);
+#define VO_PICP_MODE_AUTO 0
+#define VO_PICP_MODE_STREAM 1
+#define VO_PICP_MODE_RESIDENT 2
+int vo_picp_set_mode(vo_picp* s, int mode);
+int vo_picp_resident_capacity(const vo_picp* s, int64_t* n_pairs_max);
 /* PICPSolver::linearize (picp_solver.cpp:56-91) at the current pose, no state change.
  * H is the full symmetric 6x6; status (nullable) gets one VO_PICP_* byte per correspondence. */
 int vo_picp_linearize(vo_picp* s, float kernel_threshold, int keep_outliers,
@@ -146,6 +162,13 @@ int vo_picp_fetch_stats(vo_picp* s, vo_picp_stats* stats_out, int n_rounds);
 int vo_picp_solve(vo_picp* s, float kernel_threshold, float damping, int keep_outliers,
                   int max_rounds, float rel_tol, int* rounds_done, vo_picp_stats* last);
 
+/* Self-test of the one arithmetic shortcut on the bit-exact path (csrc/picp.cu pair_front, vo_device.cuh
+ * picp_project): rcp.approx + one FMA Newton step in place of the IEEE reciprocal of src/camera.h:30 /
+ * src/picp_solver.cpp:44 inside the gate 1e-30 <= z <= 1e30.  Runs ALL 2^32 float bit patterns on the device
+ * against __frcp_rn and 1.f / z.  out[0] = inputs inside the gate, out[1] / out[2] = mismatches of the packed /
+ * scalar form (must be 0), out[3] = first mismatching bit pattern + 1 (0: none). */
+int vo_selftest_reciprocal(vo_ctx* ctx, uint64_t out[4]);
+
 /* --------------------------------------------------------------- match_points
  * match_points<P1,P2> (src/my_utilities.h:70-120): for every row i of A the best and second
  * best squared descriptor distance over all rows of B (float32, Eigen's evaluation order),
@@ -165,6 +188,18 @@ int vo_match_dev(vo_ctx* ctx, const float* d_descA, int64_t n1, const float* d_d
                  int64_t row_begin, int64_t row_end,
                  int32_t* d_pairs_out, int64_t capacity, int64_t* n_out, int64_t stats[2],
                  float* d_best, float* d_second, int32_t* d_best_idx);
+
+/* Which of the matcher's paths runs (diagnostics, parity tests and bench.py; every path returns the identical
+ * bit-exact result): AUTO picks by size; BRUTE = the plain tiled distance-matrix scan over ALL n1*n2 pairs
+ * (any dim); ORDERED = Morton-ordered rows + packed exact scan with the early-exit bound (dim 10);
+ * INDEXED_EXACT = Morton index walk, every visited tile evaluated in exact fp32 (dim 10, large sets);
+ * INDEXED_FILTERED = the same walk behind the bf16 tensor-core lower-bound filter (what AUTO uses at scale). */
+#define VO_MATCH_PATH_AUTO 0
+#define VO_MATCH_PATH_BRUTE 1
+#define VO_MATCH_PATH_ORDERED 2
+#define VO_MATCH_PATH_INDEXED_EXACT 3
+#define VO_MATCH_PATH_INDEXED_FILTERED 4
+int vo_match_set_path(vo_ctx* ctx, int path);
 
 /* ---------------------------------------------------------------------- Cam
  * Cam::triangulatePoints (src/cam.cpp:94-140): P = K*T^-1[0:3], OpenCV DLT in double per pair,

@@ -232,3 +232,70 @@ def test_match_large_properties(ctx, oracle):
         rp, _, rb, rs, ri = oracle.match(A, B, row_begin=int(r), row_end=int(r) + 1, want_rows=True, n_threads=8)
         assert ri[0] == idx[r] and rb[0] == best[r] and rs[0] == second[r]
         assert (len(rp) == 1) == bool((pairs[:, 0] == r).any())
+
+
+def test_match_full_config4_all_rows(ctx, oracle):
+    """BASELINE config 4 AT FULL SIZE, the workload bench.py times: 1,048,576 x 1,048,576, D = 10.  The indexed,
+    tensor-core-filtered path (what AUTO runs) against the index-free exact scan (match_scan10_kernel: every column
+    is a candidate, Eigen's order, itself oracle-tested above) on ALL rows - best, second best, index and the accepted
+    pairs bit for bit - and against the CPU oracle on 4096 sampled rows."""
+    n1 = n2 = 1 << 20
+    A, B = synth.descriptors(n1, n2, seed=42)
+    ctx.match_set_path(ctx.MATCH_INDEXED_FILTERED)
+    pairs, best, second, idx = _rows_dev(ctx, A, B)
+    ctx.match_set_path(ctx.MATCH_ORDERED)
+    try:
+        pairs_x, best_x, second_x, idx_x = _rows_dev(ctx, A, B)
+    finally:
+        ctx.match_set_path(ctx.MATCH_AUTO)
+    assert np.array_equal(idx, idx_x)
+    assert np.array_equal(best.view(np.uint32), best_x.view(np.uint32))
+    assert np.array_equal(second.view(np.uint32), second_x.view(np.uint32))
+    assert np.array_equal(pairs, pairs_x)
+    assert 0.85 * n1 < len(pairs) < 0.95 * n1  # ~90 % of the rows are exact copies of a column
+    sample = np.sort(np.random.default_rng(1).choice(n1, 4096, replace=False))
+    rp, _, rb, rs, ri = oracle.match(np.ascontiguousarray(A[sample]), B, want_rows=True, n_threads=16)
+    assert np.array_equal(ri, idx[sample])
+    assert np.array_equal(rb.view(np.uint32), best[sample].view(np.uint32))
+    assert np.array_equal(rs.view(np.uint32), second[sample].view(np.uint32))
+    accepted = np.zeros(n1, bool)
+    accepted[pairs[:, 0]] = True
+    ref_acc = np.zeros(len(sample), bool)
+    ref_acc[rp[:, 0]] = True
+    assert np.array_equal(accepted[sample], ref_acc)
+
+
+@pytest.mark.parametrize("path", [1, 2, 3, 4])
+def test_match_paths_agree(ctx, oracle, path):
+    """every selectable path (plain brute force, ordered exact scan, indexed exact, indexed + tensor-core filter)
+    returns the oracle's (pairs, best, second, index) on a set large enough for the index"""
+    A, B = synth.descriptors(9000, 20000, seed=77, noise=0.03, dup_frac=0.05)
+    rp, _, rb, rs, ri = oracle.match(A, B, want_rows=True, n_threads=8)
+    ctx.match_set_path(path)
+    try:
+        pairs, best, second, idx = _rows_dev(ctx, A, B)
+    finally:
+        ctx.match_set_path(0)
+    assert np.array_equal(pairs, rp) and np.array_equal(idx, ri)
+    assert np.array_equal(best.view(np.uint32), rb.view(np.uint32))
+    assert np.array_equal(second.view(np.uint32), rs.view(np.uint32))
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_match_pruning_hostile_sets(ctx, oracle, seed):
+    """Data the index cannot prune and the bf16 bound cannot separate (all columns in a few tight clusters, rows at a
+    common distance from them): the filtered path falls back to evaluating whole tiles outright (the dense-tile guard of
+    match_scan10_mma_kernel) and must still return the oracle's result bit for bit."""
+    rng = np.random.default_rng(seed)
+    n1, n2 = 9000, 30000
+    cent = rng.uniform(-1, 1, (4, 10))
+    B = (cent[rng.integers(0, 4, n2)] + rng.normal(0, 0.004, (n2, 10))).astype(np.float32)
+    A = (cent[rng.integers(0, 4, n1)] + rng.normal(0, [0.15, 0.01][seed - 1], (n1, 10))).astype(np.float32)
+    B[rng.integers(0, n2, 200)] = B[rng.integers(0, n2, 200)]  # exact duplicates inside the clusters: lowest index wins
+    A[:500] = B[rng.integers(0, n2, 500)]
+    rp, _, rb, rs, ri = oracle.match(A, B, 0.2, 0.8, want_rows=True, n_threads=8)
+    pairs, best, second, idx = _rows_dev(ctx, A, B)
+    assert np.array_equal(idx, ri)
+    assert np.array_equal(best.view(np.uint32), rb.view(np.uint32))
+    assert np.array_equal(second.view(np.uint32), rs.view(np.uint32))
+    assert np.array_equal(pairs, rp)

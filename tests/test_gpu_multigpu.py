@@ -39,7 +39,7 @@ def _worker(rank, world, port, out_dir):
     fr = synth.picp_frame(n=400003, seed=9, permute=True)
     lo, hi = vo.shard_range(len(fr["pairs"]), world, rank)
     res = {}
-    for mode in ("nccl", "peer"):
+    for mode in ("nccl", "peer", "peer_resident"):
         if mode == "peer":
             mine = torch.from_numpy(ctx.peer_export()).to(dev)
             allh = [torch.zeros(64, dtype=torch.uint8, device=dev) for _ in range(world)]
@@ -47,6 +47,9 @@ def _worker(rank, world, port, out_dir):
             ctx.peer_attach(world, rank, torch.stack(allh).cpu().numpy())
             assert ctx.peer_active
         s = ctx.picp()
+        # "nccl" and "peer": one launch per round (ncclAllReduce / fused mailbox exchange in the last CTA);
+        # "peer_resident": all rounds in ONE persistent launch per GPU, the shard resident in shared memory
+        s.set_mode(vo.MODE_RESIDENT if mode == "peer_resident" else vo.MODE_STREAM)
         s.set_camera(fr["K"], 480, 640, fr["pose0"])
         s.set_points(fr["world"], fr["image"])
         s.set_correspondences(fr["pairs"][lo:hi])
@@ -77,6 +80,7 @@ def test_sharded_picp_nccl_and_fused_peer_exchange(tmp_path):
     ctx = vo.Context(0)
     fr = synth.picp_frame(n=400003, seed=9, permute=True)
     s = ctx.picp()
+    s.set_mode(vo.MODE_STREAM)
     s.set_camera(fr["K"], 480, 640, fr["pose0"])
     s.set_points(fr["world"], fr["image"])
     s.set_correspondences(fr["pairs"])
@@ -84,7 +88,7 @@ def test_sharded_picp_nccl_and_fused_peer_exchange(tmp_path):
     s.enqueue_rounds(3000.0, 1.0, False, 6)
     st = s.fetch_stats(6)
     single_n = np.array([x.num_inliers for x in st])
-    for mode in ("nccl", "peer"):
+    for mode in ("nccl", "peer", "peer_resident"):
         # every rank ends with the identical state, no broadcast
         assert np.array_equal(r0[mode + "_pose"], r1[mode + "_pose"])
         assert np.array_equal(r0[mode + "_n"], r1[mode + "_n"]) and np.array_equal(r0[mode + "_chi"], r1[mode + "_chi"])

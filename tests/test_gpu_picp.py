@@ -22,8 +22,9 @@ def ctx():
     c.close()
 
 
-def _solver(ctx, fr, pose=None):
+def _solver(ctx, fr, pose=None, mode=0):
     s = ctx.picp()
+    s.set_mode(mode)
     s.set_camera(fr["K"], fr["rows"], fr["cols"], fr["pose0"] if pose is None else pose)
     s.set_points(fr["world"], fr["image"])
     s.set_correspondences(fr["pairs"])
@@ -166,14 +167,16 @@ def test_empty_and_invalid_correspondences(ctx):
     s2.close()
 
 
+@pytest.mark.parametrize("mode", [1, 2], ids=["stream", "resident"])
 @pytest.mark.parametrize("n,permute,thr,keep,rounds", [(50000, False, 3000.0, False, 10), (50000, True, 100.0, True, 10),
                                                        (120, False, 3000.0, False, 8), (300000, False, 1000.0, False, 5)])
-def test_rounds_track_oracle(ctx, oracle, n, permute, thr, keep, rounds):
+def test_rounds_track_oracle(ctx, oracle, n, permute, thr, keep, rounds, mode):
     """oneRound x rounds: same inlier counts every round, pose within 1e-5 of the float32-sequential
-    oracle, both through the synchronous call and through the enqueue/fetch path."""
+    oracle, both through the synchronous call and through the enqueue/fetch path - on the streaming kernel
+    (one launch per round) and on the resident kernel (all rounds in one persistent launch)."""
     fr = synth.picp_frame(n=n, seed=n + 1, permute=permute)
-    s = _solver(ctx, fr)
-    s2 = _solver(ctx, fr)
+    s = _solver(ctx, fr, mode=mode)
+    s2 = _solver(ctx, fr, mode=mode)
     pose = fr["pose0"].copy()
     s2.enqueue_rounds(thr, 1.0, keep, rounds)
     batch = s2.fetch_stats(rounds)
@@ -194,12 +197,13 @@ def test_rounds_track_oracle(ctx, oracle, n, permute, thr, keep, rounds):
     s2.close()
 
 
-def test_device_side_convergence_loop(ctx, oracle):
+@pytest.mark.parametrize("mode", [1, 2], ids=["stream", "resident"])
+def test_device_side_convergence_loop(ctx, oracle, mode):
     """vo_picp_solve == the driver loop of exec/icp_test.cpp:88-107 run with synchronous rounds."""
     fr = synth.picp_frame(n=20000, seed=11)
-    s = _solver(ctx, fr)
+    s = _solver(ctx, fr, mode=mode)
     done, last = s.solve(3000.0, 1.0, False, max_rounds=50, rel_tol=1e-3)
-    s2 = _solver(ctx, fr)
+    s2 = _solver(ctx, fr, mode=mode)
     prev = np.float32(np.finfo(np.float32).max)
     it = 0
     for it in range(1, 51):
@@ -232,6 +236,154 @@ def test_device_resident_points(ctx, oracle):
     ref = oracle.linearize(fr["K"], 480, 640, fr["pose0"], fr["world"], fr["image"], fr["pairs"], 3000.0, False,
                            accum="f64")
     _check_lin(lin, ref)
+    s.close()
+
+
+def _sizes_around_resident_geometry(cap):
+    # 1 CTA / 2 CTAs boundary (1536 quads-threads x 4), ragged tails, one wave, the capacity itself
+    return [1, 3, 5, 1535, 1536, 1537, 6143, 6145, 50001, 148 * 1536 + 7, 1 << 20, cap - 3, cap]
+
+
+def test_resident_matches_streaming(ctx, oracle):
+    """The persistent shared-memory-resident kernel against the one-launch-per-round kernel on the same frames:
+    identical inlier / outlier counts in round 0 (same arithmetic on the exact part), every later round within the
+    knife-edge slack, chi within 1e-5, final pose within 1e-6; and round 0 against the oracle's counts."""
+    probe = ctx.picp()
+    cap = probe.resident_capacity
+    probe.close()
+    assert cap >= 1310720  # BASELINE config 3's 10M frame over 8 GPUs must fit
+    for n in _sizes_around_resident_geometry(cap):
+        permute = n % 2 == 1
+        thr, keep = ((3000.0, False), (100.0, True))[(n // 3) % 2]
+        fr = synth.picp_frame(n=n, seed=7 + n, permute=permute)
+        res = {}
+        for mode in (1, 2):
+            s = _solver(ctx, fr, mode=mode)
+            s.enqueue_rounds(thr, 1.0, keep, 6)
+            res[mode] = (s.fetch_stats(6), s.get_pose())
+            s.close()
+        (st1, p1), (st2, p2) = res[1], res[2]
+        ref = oracle.linearize(fr["K"], 480, 640, fr["pose0"], fr["world"], fr["image"], fr["pairs"], thr, keep, accum="f64")
+        assert st2[0].num_inliers == ref["n_inliers"] == st1[0].num_inliers, n
+        assert st2[0].num_outliers == st1[0].num_outliers, n
+        for r in range(6):
+            slack = 0 if r == 0 else max(2, int(1e-5 * n))
+            assert abs(st1[r].num_inliers - st2[r].num_inliers) <= slack, (n, r)
+            assert abs(st1[r].chi_inliers - st2[r].chi_inliers) <= 1e-5 * max(st1[r].chi_inliers, 1.0), (n, r)
+        assert np.abs(p1 - p2).max() <= 1e-6, n
+
+
+def test_resident_capacity_and_fallback(ctx):
+    """a set one correspondence above the resident capacity: AUTO streams it, RESIDENT refuses it"""
+    vo = product()
+    probe = ctx.picp()
+    cap = probe.resident_capacity
+    probe.close()
+    fr = synth.picp_frame(n=cap + 1, seed=5)
+    s = _solver(ctx, fr, mode=0)
+    s.enqueue_rounds(3000.0, 1.0, False, 3)
+    auto = (s.fetch_stats(3), s.get_pose())
+    s.set_mode(2)
+    s.set_pose(fr["pose0"])
+    with pytest.raises(vo.VoError):
+        s.enqueue_rounds(3000.0, 1.0, False, 3)
+    s.set_mode(1)
+    s.set_pose(fr["pose0"])
+    s.enqueue_rounds(3000.0, 1.0, False, 3)
+    assert np.array_equal(s.get_pose(), auto[1])
+    s.close()
+
+
+def test_resident_is_deterministic_and_restartable(ctx):
+    """two solves of the same frame on one handle (the word buffers' sequence numbers keep counting) and on a fresh
+    handle give bit-identical stats and poses; rounds split over two calls equal one call"""
+    fr = synth.picp_frame(n=300001, seed=21, permute=True)
+    s = _solver(ctx, fr, mode=2)
+    outs = []
+    for rep in range(3):
+        s.set_pose(fr["pose0"])
+        s.enqueue_rounds(3000.0, 1.0, False, 8)
+        st = s.fetch_stats(8)
+        outs.append(([x.chi_inliers for x in st], [x.num_inliers for x in st], s.get_pose()))
+    s.set_pose(fr["pose0"])
+    s.enqueue_rounds(3000.0, 1.0, False, 3)
+    s.enqueue_rounds(3000.0, 1.0, False, 5)
+    st = s.fetch_stats(5)
+    split_pose = s.get_pose()
+    s.close()
+    s2 = _solver(ctx, fr, mode=2)
+    s2.enqueue_rounds(3000.0, 1.0, False, 8)
+    st2 = s2.fetch_stats(8)
+    outs.append(([x.chi_inliers for x in st2], [x.num_inliers for x in st2], s2.get_pose()))
+    s2.close()
+    for o in outs[1:]:
+        assert o[0] == outs[0][0] and o[1] == outs[0][1] and np.array_equal(o[2], outs[0][2])
+    assert np.array_equal(split_pose, outs[0][2])
+    assert [x.num_inliers for x in st] == outs[0][1][3:]
+
+
+@pytest.mark.parametrize("mode", [1, 2], ids=["stream", "resident"])
+def test_out_of_range_index_on_the_device_path(ctx, mode):
+    """set_correspondences_dev cannot validate synchronously: the bad index is reported by the next fetch / solve,
+    and a following valid set works (the flag does not stick)."""
+    import torch
+    vo = product()
+    fr = synth.picp_frame(n=5000, seed=3)
+    bad = fr["pairs"].copy()
+    bad[1234, 1] = 5000
+    dw, di = torch.from_numpy(fr["world"]).cuda(), torch.from_numpy(fr["image"]).cuda()
+    dbad, dgood = torch.from_numpy(bad).cuda(), torch.from_numpy(fr["pairs"]).cuda()
+    torch.cuda.synchronize()
+    s = ctx.picp()
+    s.set_mode(mode)
+    s.set_camera(fr["K"], 480, 640, fr["pose0"])
+    s.set_points_dev(dw.data_ptr(), 5000, di.data_ptr(), 5000)
+    s.set_correspondences_dev(dbad.data_ptr(), 5000)
+    s.enqueue_rounds(3000.0, 1.0, False, 3)
+    with pytest.raises(vo.VoError, match="out of range"):
+        s.fetch_stats(3)
+    s.set_pose(fr["pose0"])
+    s.set_correspondences_dev(dgood.data_ptr(), 5000)
+    s.enqueue_rounds(3000.0, 1.0, False, 3)
+    st = s.fetch_stats(3)
+    assert st[-1].num_inliers > 4000
+    s.close()
+
+
+def test_reciprocal_shortcut_exhaustive(ctx):
+    """rcp.approx + one FMA Newton step == the correctly rounded reciprocal (__frcp_rn == 1.f / z) for EVERY float
+    inside the gate 1e-30 <= z <= 1e30 that pair_front / picp_project apply it under: all 2^32 bit patterns."""
+    in_gate, bad_packed, bad_scalar, first = ctx.selftest_reciprocal()
+    lo = np.array([1e-30], np.float32).view(np.uint32)[0]
+    hi = np.array([1e30], np.float32).view(np.uint32)[0]
+    assert in_gate == int(hi) - int(lo) + 1  # every positive float in the gate was visited exactly once
+    assert bad_packed == 0 and bad_scalar == 0, f"first mismatch at bit pattern {first - 1:#x}"
+
+
+@pytest.mark.parametrize("n", [1 << 20, 10 * (1 << 20)])
+@pytest.mark.parametrize("permute", [False, True], ids=["identity", "permuted"])
+def test_benchmarked_sizes_match_oracle(ctx, oracle, n, permute):
+    """BASELINE configs 2 and 3 AT FULL SIZE (1,048,576 and 10,485,760 correspondences, variant A identity and variant
+    B permuted world indices): per-correspondence status bit-exact, counts exact, H / b / chi <= 1e-4 against the
+    float64-accumulated oracle - for thr 3000 with inlier rejection and for thr 100 with kept outliers (the lambda
+    branch, src/picp_solver.cpp:77-80)."""
+    fr = synth.picp_frame(n=n, seed=42, permute=permute)
+    s = _solver(ctx, fr)
+    for thr, keep in ((3000.0, False), (100.0, True)):
+        lin = s.linearize(thr, keep, want_status=True, n_pairs=n)
+        ref = oracle.linearize(fr["K"], 480, 640, fr["pose0"], fr["world"], fr["image"], fr["pairs"], thr, keep,
+                               accum="f64")
+        _check_lin(lin, ref)
+    # ten rounds (the benchmarked step): counts of every round within the knife-edge slack of the oracle's, pose 1e-5
+    s.enqueue_rounds(3000.0, 1.0, False, 10)
+    st = s.fetch_stats(10)
+    pose = fr["pose0"].copy()
+    for r in range(10):
+        pose, ci, co, ni = oracle.one_round(fr["K"], 480, 640, pose, fr["world"], fr["image"], fr["pairs"], 3000.0, 1.0,
+                                            False, n_threads=16)
+        slack = 0 if r == 0 else max(2, int(1e-5 * n))
+        assert abs(st[r].num_inliers - ni) <= slack, r
+    assert np.abs(s.get_pose() - pose).max() <= POSE_TOL
     s.close()
 
 
