@@ -106,6 +106,8 @@ _sig("vo_selftest_reciprocal", C.c_int, _vp, _vp)
 _sig("vo_triangulate", C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp)
 _sig("vo_triangulate_dev", C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp)
 _sig("vo_essential_recover", C.c_int, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, C.POINTER(C.c_int))
+_sig("vo_essential_recover_ex", C.c_int, _vp, _vp, _vp, _vp, _i64, C.c_int, C.c_double, C.c_double, C.c_int, _vp, _vp, _vp,
+     _vp, C.POINTER(C.c_int), _vp, C.POINTER(C.c_int), C.POINTER(C.c_int))
 _sig("vo_anti_join", C.c_int, _vp, _vp, _i64, _vp, _i64, _vp, C.POINTER(_i64))
 _sig("vo_seq_batch_run", C.c_int, _vp, C.POINTER(SeqParams), C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp,
      _vp, _vp, _vp, _vp, _vp, _vp, _vp)
@@ -306,17 +308,23 @@ class Context:
                                           _p(_f32(T2).reshape(12)), _p(d_x1), _p(d_x2), n, _p(d_out)),
                     "vo_triangulate_dev")
 
-    def essential_recover(self, K, x1, x2):
+    def essential_recover(self, K, x1, x2, method="ransac", prob=0.999, threshold=1.0, max_iters=1000, full=False):
+        """src/cam.cpp:37-91. method "ransac": cv::findEssentialMat(RANSAC) restated (the reference's call);
+        "8pt": normalised linear estimator on all matches. full=True also returns (ransac_mask, inliers, iterations)."""
         x1 = _f32(x1).reshape(-1, 2)
         x2 = _f32(x2).reshape(-1, 2)
         E = np.zeros(9)
         R = np.zeros(9)
         t = np.zeros(3)
         mask = np.zeros(max(len(x1), 1), np.uint8)
-        good = C.c_int(0)
-        self._check(_L.vo_essential_recover(self._h, _p(_f32(K).reshape(9)), _p(x1), _p(x2), len(x1), _p(E), _p(R),
-                                            _p(t), _p(mask), C.byref(good)), "vo_essential_recover")
-        return E.reshape(3, 3), R.reshape(3, 3), t, mask[: len(x1)], good.value
+        rmask = np.zeros(max(len(x1), 1), np.uint8)
+        good, rin, rit = C.c_int(0), C.c_int(0), C.c_int(0)
+        self._check(_L.vo_essential_recover_ex(self._h, _p(_f32(K).reshape(9)), _p(x1), _p(x2), len(x1),
+                                               0 if method == "ransac" else 1, prob, threshold, max_iters, _p(E), _p(R),
+                                               _p(t), _p(mask), C.byref(good), _p(rmask), C.byref(rin), C.byref(rit)),
+                    "vo_essential_recover")
+        out = (E.reshape(3, 3), R.reshape(3, 3), t, mask[: len(x1)], good.value)
+        return out + (rmask[: len(x1)], rin.value, rit.value) if full else out
 
     # ---- batched independent sequences (BASELINE config 5)
     def seq_batch_run(self, params, cnt, uv, desc, id_real, world_cap=1024):

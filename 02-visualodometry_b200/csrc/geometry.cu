@@ -13,9 +13,10 @@
 // These are latency / FP64-issue bound, not HBM bound: one thread per correspondence, no shared
 // staging; small dense solves (9x9 eigen, 3x3 SVD) run on one thread between the data-parallel
 // passes so nothing returns to the host mid-pipeline.
-#include "vo_device.cuh"
+#include "five_point.cuh"
 
 #include <float.h>
+#include <algorithm>
 #include <math.h>
 
 namespace {
@@ -120,6 +121,118 @@ __global__ void essential_pick_kernel(EssState* st) {
   for (int k = 0; k < 3; ++k) st->tt[k] = sg * st->t[k];
   st->pick = pick;
   st->n_good = g[pick];
+}
+
+// ---------------------------------------------------------------- essential: cv::findEssentialMat(RANSAC) restated
+// OpenCV's loop is sequential (sample, solve, count inliers, maybe shrink the iteration budget); here a batch of
+// samples is solved and scored in parallel (one thread per minimal sample, one CTA per hypothesis for the Sampson
+// counts) and ONE thread then replays OpenCV's bookkeeping over the batch in sample order, so the winner, the
+// iteration count and the tie-breaks are those of the sequential loop (ptsetreg.cpp RANSACPointSetRegistrator::run).
+constexpr int kMaxModels = 10;
+
+struct Ransac5State {
+  int iter;      // samples consumed (OpenCV's `iter`)
+  int niters;    // current iteration budget
+  int max_good;
+  int done;
+  int best_sample, best_model;
+  double E[9];
+};
+
+__global__ void ess5_init_kernel(Ransac5State* st, int max_iters) {
+  if (threadIdx.x != 0) return;
+  st->iter = 0;
+  st->niters = max_iters > 1 ? max_iters : 1;
+  st->max_good = 0;
+  st->done = 0;
+  st->best_sample = st->best_model = -1;
+  for (int k = 0; k < 9; ++k) st->E[k] = 0;
+}
+
+// (x - c) / f exactly as findEssentialMat's matrix expression evaluates it: x * (1/f) + (-c * (1/f))
+__device__ __forceinline__ double ess5_norm(float x, double inv_f, double c) { return (double)x * inv_f + (-c * inv_f); }
+
+__global__ void __launch_bounds__(32) ess5_solve_kernel(EssCam cam, const float2* __restrict__ x1,
+                                                       const float2* __restrict__ x2, const int* __restrict__ subsets,
+                                                       int s0, int count, double* __restrict__ models,
+                                                       int* __restrict__ n_models, const Ransac5State* st) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= count || st->done) return;
+  const double ifx = 1.0 / cam.fx, ify = 1.0 / cam.fy;
+  double q1[10], q2[10];
+  for (int i = 0; i < 5; ++i) {
+    const int id = subsets[5 * (s0 + b) + i];
+    const float2 p = __ldg(x1 + id), q = __ldg(x2 + id);
+    q1[2 * i] = ess5_norm(p.x, ifx, cam.cx);
+    q1[2 * i + 1] = ess5_norm(p.y, ify, cam.cy);
+    q2[2 * i] = ess5_norm(q.x, ifx, cam.cx);
+    q2[2 * i + 1] = ess5_norm(q.y, ify, cam.cy);
+  }
+  n_models[b] = five_point_dev(q1, q2, models + (size_t)b * kMaxModels * 9);
+}
+
+// blockIdx.x = sample * kMaxModels + model: number of correspondences with Sampson error <= t (float compare)
+__global__ void __launch_bounds__(128) ess5_score_kernel(EssCam cam, const float2* __restrict__ x1,
+                                                        const float2* __restrict__ x2, long long n,
+                                                        const double* __restrict__ models, const int* __restrict__ n_models,
+                                                        float t, int* __restrict__ counts, const Ransac5State* st) {
+  const int b = blockIdx.x / kMaxModels, m = blockIdx.x % kMaxModels;
+  if (st->done || m >= n_models[b]) return;
+  __shared__ double sE[9];
+  __shared__ int s_cnt;
+  if (threadIdx.x < 9) sE[threadIdx.x] = models[((size_t)b * kMaxModels + m) * 9 + threadIdx.x];
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
+  const double ifx = 1.0 / cam.fx, ify = 1.0 / cam.fy;
+  int good = 0;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    const float2 p = __ldg(x1 + i), q = __ldg(x2 + i);
+    good += sampson_dev(sE, ess5_norm(p.x, ifx, cam.cx), ess5_norm(p.y, ify, cam.cy), ess5_norm(q.x, ifx, cam.cx),
+                        ess5_norm(q.y, ify, cam.cy)) <= t;
+  }
+  good = warp_sum_i(good);
+  if ((threadIdx.x & 31) == 0 && good) atomicAdd(&s_cnt, good);  // integer sum: order independent
+  __syncthreads();
+  if (threadIdx.x == 0) counts[blockIdx.x] = s_cnt;
+}
+
+// OpenCV's sequential bookkeeping over one batch (ptsetreg.cpp:run): a hypothesis replaces the best one only when it
+// has strictly more inliers (the first best wins ties), every improvement shrinks the iteration budget, and sample
+// `iter` is looked at only while iter < niters
+__global__ void ess5_select_kernel(Ransac5State* st, const double* __restrict__ models, const int* __restrict__ n_models,
+                                   const int* __restrict__ counts, int s0, int count, long long n, double prob) {
+  if (threadIdx.x != 0 || st->done) return;
+  for (int b = 0; b < count; ++b) {
+    if (st->iter >= st->niters) break;
+    for (int m = 0; m < n_models[b]; ++m) {
+      const int good = counts[b * kMaxModels + m];
+      if (good > max(st->max_good, 4)) {
+        st->max_good = good;
+        st->best_sample = s0 + b;
+        st->best_model = m;
+        for (int k = 0; k < 9; ++k) st->E[k] = models[((size_t)b * kMaxModels + m) * 9 + k];
+        st->niters = ransac_update_num_iters(prob, (double)(n - good) / (double)n, 5, st->niters);
+      }
+    }
+    st->iter++;
+  }
+  if (st->iter >= st->niters) st->done = 1;
+}
+
+// inlier mask of the winning hypothesis (findEssentialMat's optional mask output: 0 / 1)
+__global__ void __launch_bounds__(128) ess5_mask_kernel(EssCam cam, const float2* __restrict__ x1,
+                                                       const float2* __restrict__ x2, long long n,
+                                                       const Ransac5State* st, float t, unsigned char* __restrict__ mask) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double ifx = 1.0 / cam.fx, ify = 1.0 / cam.fy;
+  const float2 p = __ldg(x1 + i), q = __ldg(x2 + i);
+  mask[i] = sampson_dev(st->E, ess5_norm(p.x, ifx, cam.cx), ess5_norm(p.y, ify, cam.cy), ess5_norm(q.x, ifx, cam.cx),
+                        ess5_norm(q.y, ify, cam.cy)) <= t;
+}
+
+__global__ void ess5_decompose_kernel(const Ransac5State* rs, EssState* st) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) essential_decompose_dev(rs->E, st);
 }
 
 // ---------------------------------------------------------------- Camera::projectPoints
@@ -248,21 +361,37 @@ int vo_triangulate(vo_ctx* ctx, const float K[9], const float T1[12], const floa
   return VO_OK;
 }
 
-int vo_essential_recover(vo_ctx* ctx, const float K[9], const float* x1, const float* x2, int64_t n, double E[9],
-                         double R[9], double t[3], uint8_t* mask, int* n_good) {
+int vo_essential_recover_ex(vo_ctx* ctx, const float K[9], const float* x1, const float* x2, int64_t n, int method,
+                            double prob, double threshold, int max_iters, double E[9], double R[9], double t[3],
+                            uint8_t* mask, int* n_good, uint8_t* ransac_mask, int* ransac_inliers, int* ransac_iters) {
   if (!ctx) return VO_ERR_INVALID;
   int st = vo_ctx_activate(ctx);
   if (st) return st;
   VO_REQUIRE(ctx, K && x1 && x2, "vo_essential_recover: null buffers");
-  VO_REQUIRE(ctx, n >= 8, "vo_essential_recover: at least 8 correspondences");
+  VO_REQUIRE(ctx, method == VO_ESSENTIAL_RANSAC5 || method == VO_ESSENTIAL_LINEAR8, "vo_essential_recover: method");
+  const bool ransac = method == VO_ESSENTIAL_RANSAC5;
+  if (ransac) {
+    VO_REQUIRE(ctx, n >= 5, "vo_essential_recover: at least 5 correspondences");
+    VO_REQUIRE(ctx, n < 0x7fffffff, "vo_essential_recover: too many correspondences");
+    VO_REQUIRE(ctx, prob > 0 && prob < 1 && threshold > 0 && max_iters >= 1 && max_iters <= 100000, "vo_essential_recover: RANSAC parameters");
+  } else {
+    VO_REQUIRE(ctx, n >= 8, "vo_essential_recover: at least 8 correspondences");
+  }
+  if (ransac_inliers) *ransac_inliers = 0;
+  if (ransac_iters) *ransac_iters = 0;
   const EssCam cam = {(double)K[0], (double)K[4], (double)K[2], (double)K[5]};
   long long blocks = (n + kEssThreads - 1) / kEssThreads;
   if (blocks > ctx->sm_count) blocks = ctx->sm_count;
+  constexpr int kBatch0 = 32, kBatch = 128;  // samples solved per launch: most clean problems stop within the first batch
   size_t off = 0;
   auto carve = [&](size_t bytes) { size_t o = off; off = vo_align_up(off + bytes, 256); return o; };
   const size_t o_x1 = carve((size_t)n * 8), o_x2 = carve((size_t)n * 8);
   const size_t o_part = carve((size_t)blocks * kMom * 8), o_state = carve(sizeof(EssState));
   const size_t o_masks = carve((size_t)n * 4);
+  const size_t o_rs = carve(sizeof(Ransac5State)), o_sub = carve(ransac ? (size_t)max_iters * 5 * 4 : 0);
+  const size_t o_models = carve(ransac ? (size_t)kBatch * kMaxModels * 9 * 8 : 0);
+  const size_t o_nm = carve(ransac ? (size_t)kBatch * 4 : 0), o_cnt = carve(ransac ? (size_t)kBatch * kMaxModels * 4 : 0);
+  const size_t o_rmask = carve(ransac ? (size_t)n : 0);
   char* base;
   st = vo_scratch(ctx, off, (void**)&base);
   if (st) return st;
@@ -273,10 +402,64 @@ int vo_essential_recover(vo_ctx* ctx, const float K[9], const float* x1, const f
   unsigned char* masks = (unsigned char*)(base + o_masks);
   VO_CUDA(ctx, cudaMemcpyAsync(dx1, x1, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
   VO_CUDA(ctx, cudaMemcpyAsync(dx2, x2, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
-  essential_moments_kernel<<<(unsigned)blocks, kEssThreads, 0, ctx->stream>>>(cam, dx1, dx2, n, part);
-  VO_CHECK_LAUNCH(ctx, "essential_moments_kernel");
-  essential_solve_kernel<<<1, 32, 0, ctx->stream>>>(part, (int)blocks, dstate);
-  VO_CHECK_LAUNCH(ctx, "essential_solve_kernel");
+  if (ransac) {
+    Ransac5State* rs = (Ransac5State*)(base + o_rs);
+    int* dsub = (int*)(base + o_sub);
+    double* models = (double*)(base + o_models);
+    int* n_models = (int*)(base + o_nm);
+    int* counts = (int*)(base + o_cnt);
+    unsigned char* rmask = (unsigned char*)(base + o_rmask);
+    // the sample sequence depends only on n: cv::RNG((uint64)-1) + getSubset, generated on the host
+    int total = max_iters;
+    if (n == 5) total = 1;  // count == modelPoints: OpenCV solves the one sample and keeps its first model
+    void* hp;
+    st = vo_pinned(ctx, (size_t)total * 5 * 4 + 256, &hp);
+    if (st) return st;
+    int* hsub = (int*)hp;
+    if (n == 5) {
+      for (int i = 0; i < 5; ++i) hsub[i] = i;
+    } else {
+      CvRng rng(~0ull);
+      for (int s_ = 0; s_ < total; ++s_) ransac_next_subset(rng, (int)n, hsub + 5 * s_);
+    }
+    VO_CUDA(ctx, cudaMemcpyAsync(dsub, hsub, (size_t)total * 5 * 4, cudaMemcpyHostToDevice, ctx->stream));
+    VO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the pinned buffer is reused for read-backs below
+    const double thr = threshold / ((cam.fx + cam.fy) / 2);
+    const float tf = (n == 5) ? 3.0e38f : (float)(thr * thr);  // (n == 5: every point counts as an inlier)
+    ess5_init_kernel<<<1, 32, 0, ctx->stream>>>(rs, total);
+    VO_CHECK_LAUNCH(ctx, "ess5_init_kernel");
+    Ransac5State hs_r;
+    for (int s0 = 0; s0 < total;) {
+      const int count = std::min(s0 == 0 ? kBatch0 : kBatch, total - s0);
+      ess5_solve_kernel<<<(count + 31) / 32, 32, 0, ctx->stream>>>(cam, dx1, dx2, dsub, s0, count, models, n_models, rs);
+      VO_CHECK_LAUNCH(ctx, "ess5_solve_kernel");
+      ess5_score_kernel<<<count * kMaxModels, 128, 0, ctx->stream>>>(cam, dx1, dx2, n, models, n_models, tf, counts, rs);
+      VO_CHECK_LAUNCH(ctx, "ess5_score_kernel");
+      ess5_select_kernel<<<1, 32, 0, ctx->stream>>>(rs, models, n_models, counts, s0, count, n, prob);
+      VO_CHECK_LAUNCH(ctx, "ess5_select_kernel");
+      s0 += count;
+      VO_CUDA(ctx, cudaMemcpyAsync(hp, rs, sizeof(Ransac5State), cudaMemcpyDeviceToHost, ctx->stream));
+      VO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      memcpy(&hs_r, hp, sizeof(hs_r));
+      if (hs_r.done) break;
+    }
+    if (ransac_iters) *ransac_iters = hs_r.iter;
+    if (ransac_inliers) *ransac_inliers = hs_r.max_good;
+    if (hs_r.max_good <= 0)  // cv::findEssentialMat returns an empty matrix; the reference exits (src/cam.cpp:56-59)
+      return vo_set_error(ctx, VO_ERR_STATE, "vo_essential_recover", "RANSAC found no essential matrix");
+    if (ransac_mask) {
+      ess5_mask_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(cam, dx1, dx2, n, rs, tf, rmask);
+      VO_CHECK_LAUNCH(ctx, "ess5_mask_kernel");
+      VO_CUDA(ctx, cudaMemcpyAsync(ransac_mask, rmask, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    ess5_decompose_kernel<<<1, 32, 0, ctx->stream>>>(rs, dstate);
+    VO_CHECK_LAUNCH(ctx, "ess5_decompose_kernel");
+  } else {
+    essential_moments_kernel<<<(unsigned)blocks, kEssThreads, 0, ctx->stream>>>(cam, dx1, dx2, n, part);
+    VO_CHECK_LAUNCH(ctx, "essential_moments_kernel");
+    essential_solve_kernel<<<1, 32, 0, ctx->stream>>>(part, (int)blocks, dstate);
+    VO_CHECK_LAUNCH(ctx, "essential_solve_kernel");
+  }
   essential_cheirality_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(cam, dx1, dx2, n, dstate, masks);
   VO_CHECK_LAUNCH(ctx, "essential_cheirality_kernel");
   essential_pick_kernel<<<1, 32, 0, ctx->stream>>>(dstate);
@@ -297,6 +480,13 @@ int vo_essential_recover(vo_ctx* ctx, const float K[9], const float* x1, const f
     VO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   }
   return VO_OK;
+}
+
+int vo_essential_recover(vo_ctx* ctx, const float K[9], const float* x1, const float* x2, int64_t n, double E[9],
+                         double R[9], double t[3], uint8_t* mask, int* n_good) {
+  // the reference's call: cv::findEssentialMat(p1, p2, K, cv::RANSAC) with OpenCV's defaults (src/cam.cpp:49)
+  return vo_essential_recover_ex(ctx, K, x1, x2, n, VO_ESSENTIAL_RANSAC5, 0.999, 1.0, 1000, E, R, t, mask, n_good,
+                                 nullptr, nullptr, nullptr);
 }
 
 int vo_project_points(vo_ctx* ctx, const float K[9], int rows, int cols, const float pose[12], const float* world_xyz,

@@ -231,10 +231,12 @@ def bench_picp(args, vo, torch, dist, ctx, dev, stream, local, rank, world, scal
             launches = ctx.kernel_launches - launches0
             # the timed region lasts only a few ms: keep the identical load running ~1 s more so that the
             # 100 ms nvidia-smi sampler sees the clocks this workload settles at (not part of the timing)
-            t_end = time.time() + 1.0
-            while time.time() < t_end:
+            # (a step COUNT every rank agrees on, not a wall-clock deadline: with peers attached every step
+            # exchanges with the other ranks, so all ranks must launch the same number of steps)
+            ms_probe = max_over_ranks(ev[0].elapsed_time(ev[1])) / steps
+            for _ in range(int(min(5000, max(10, 1000.0 / max(ms_probe, 1e-3))))):
                 step_resident()
-                torch.cuda.synchronize()
+            torch.cuda.synchronize()
     else:
         timed()
         launches = ctx.kernel_launches - launches0
@@ -469,16 +471,21 @@ def bench_matching(args, ctx, vo, torch, dev, rank, world, barrier, max_over_ran
     rows = hi - lo
     pairs = torch.empty((rows, 2), dtype=torch.int32, device=dev)
 
-    def timed(dAx, r, dBx, steps):
+    def timed(dAx, r, dBx, steps, collective=False):
+        """collective=True: every rank calls this (barrier, max over ranks); False: this rank alone (no collectives)"""
         ctx.match_dev(dAx.data_ptr(), r, dBx.data_ptr(), n2, 10, pairs.data_ptr(), rows)  # warm-up
-        barrier()
+        if collective:
+            barrier()
+        else:
+            torch.cuda.synchronize()
         t0 = time.perf_counter()
         for _ in range(steps):
             n, _ = ctx.match_dev(dAx.data_ptr(), r, dBx.data_ptr(), n2, 10, pairs.data_ptr(), rows)
         torch.cuda.synchronize()
-        return max_over_ranks(time.perf_counter() - t0) / steps, n
+        dt_ = time.perf_counter() - t0
+        return (max_over_ranks(dt_) if collective else dt_) / steps, n
 
-    dt, n = timed(dA, rows, dB, 5)
+    dt, n = timed(dA, rows, dB, 5, collective=True)
     # the same shard through the host-buffer entry point (vo_match: device staging, H2D of A-shard and B, D2H of pairs)
     Ah, Bh = np.ascontiguousarray(A[lo:hi]), B
     ctx.match(Ah, Bh)

@@ -32,11 +32,89 @@ def padd(p, q, s=1.0):
         r[m] = r.get(m, 0.0) + s*c
     return r
 
+def cv_null_basis(Q):
+    """rows 5..8 of Vt of cv::SVD::compute(Q 5x9, MODIFY_A | FULL_UV) (lapack.cpp JacobiSVDImpl_: the rows of Q are
+    orthogonalised by one-sided Jacobi, sorted by norm; the 4 missing rows are +-1/9 sign vectors from
+    RNG(0x12345678), Gram-Schmidt'ed twice against all previous rows, normalised)."""
+    m, n, n1 = 9, 5, 9
+    At = np.zeros((9, 9)); At[:5] = Q
+    eps = np.finfo(np.float64).eps * 10
+    W = (At[:5]**2).sum(1)
+    for it in range(max(m, 30)):
+        changed = False
+        for i in range(n-1):
+            for j in range(i+1, n):
+                a, b = W[i], W[j]
+                p = float(At[i] @ At[j])
+                if abs(p) <= eps*np.sqrt(a*b): continue
+                p *= 2
+                beta = a - b; gamma = np.hypot(p, beta)
+                if beta < 0:
+                    delta = (gamma - beta)*0.5
+                    s_ = np.sqrt(delta/gamma); c_ = p/(gamma*s_*2)
+                else:
+                    c_ = np.sqrt((gamma + beta)/(gamma*2)); s_ = p/(gamma*c_*2)
+                t0 = c_*At[i] + s_*At[j]; t1 = -s_*At[i] + c_*At[j]
+                At[i], At[j] = t0, t1
+                W[i], W[j] = (t0**2).sum(), (t1**2).sum()
+                changed = True
+        if not changed: break
+    W = np.sqrt((At[:5]**2).sum(1))
+    for i in range(n-1):
+        j = i
+        for k in range(i+1, n):
+            if W[j] < W[k]: j = k
+        if i != j:
+            W[[i, j]] = W[[j, i]]; At[[i, j]] = At[[j, i]]
+    rng = RNG(0x12345678)
+    tiny = sys.float_info.min
+    for i in range(n1):
+        sd = W[i] if i < n else 0.0
+        ii = 0
+        while ii < 100 and sd <= tiny:
+            val0 = 1.0/m
+            for k in range(m):
+                At[i, k] = val0 if (rng.next() & 256) != 0 else -val0
+            for _ in range(2):
+                for j in range(i):
+                    sd = float(At[i] @ At[j])
+                    At[i] = At[i] - sd*At[j]
+                    asum = np.abs(At[i]).sum()
+                    asum = 1/asum if asum > eps*100 else 0.0
+                    At[i] *= asum
+            sd = np.sqrt((At[i]**2).sum())
+            ii += 1
+        At[i] *= (1/sd if sd > tiny else 0.0)
+    return At[5:9].copy()
+
+def cv_solve_poly(c, max_iters=300):
+    """cv::solvePoly (mathfuncs.cpp): Durand-Kerner, roots initialised to (1+i)^k, updated in place, 300 sweeps.
+    c[k] = coefficient of z^k. Returns the roots in OpenCV's order."""
+    n = len(c) - 1
+    while n > 1 and abs(c[n]) <= np.finfo(np.float64).eps: n -= 1
+    roots = []
+    p = complex(1, 0); r = complex(1, 1)
+    for i in range(n):
+        roots.append(p); p = p*r
+    for it in range(max_iters):
+        max_diff = 0.0
+        for i in range(n):
+            p = roots[i]
+            num = complex(c[n]); den = complex(c[n])
+            for j in range(n):
+                num = num*p + c[n-j-1]
+                if j != i and p != roots[j]:
+                    den = den*(p - roots[j])
+            num = num/den
+            roots[i] = p - num
+            max_diff = max(max_diff, abs(num))
+        if max_diff <= 0: break
+    return roots
+
 def five_point(q1, q2):
     """q1, q2: 5x2 normalised points. Returns list of 3x3 E (unit Frobenius)."""
-    Q = np.stack([q2[:,0]*q1[:,0], q2[:,1]*q1[:,0], q1[:,0], q2[:,0]*q1[:,1], q2[:,1]*q1[:,1], q1[:,1], q2[:,0], q2[:,1], np.ones(5)], 1)
-    _, _, Vt = np.linalg.svd(Q, full_matrices=True)
-    EE = Vt[5:9]  # 4 x 9 null-space basis (rows)
+    Q = np.stack([q2[:,0]*q1[:,0], q2[:,0]*q1[:,1], q2[:,0], q2[:,1]*q1[:,0], q2[:,1]*q1[:,1], q2[:,1], q1[:,0], q1[:,1], np.ones(5)], 1)
+    EE = cv_null_basis(Q)  # 4 x 9 null-space basis (rows), OpenCV's
     # E(x,y,z) = x E0 + y E1 + z E2 + E3, entries are degree-1 polynomials
     Ep = [[{(1,0,0): EE[0,3*i+j], (0,1,0): EE[1,3*i+j], (0,0,1): EE[2,3*i+j], (0,0,0): EE[3,3*i+j]} for j in range(3)] for i in range(3)]
     # det E
@@ -76,7 +154,8 @@ def five_point(q1, q2):
     P = [[np.poly1d(B[j, 0:4]), np.poly1d(B[j, 4:8]), np.poly1d(B[j, 8:13])] for j in range(3)]
     det = (P[0][0]*(P[1][1]*P[2][2] - P[1][2]*P[2][1]) - P[0][1]*(P[1][0]*P[2][2] - P[1][2]*P[2][0])
            + P[0][2]*(P[1][0]*P[2][1] - P[1][1]*P[2][0]))
-    roots = np.roots(det.coeffs)
+    cc = np.zeros(11); cc[:len(det.coeffs)] = det.coeffs[::-1]
+    roots = cv_solve_poly(cc)
     Es = []
     for rt in roots:
         if abs(rt.imag) > 1e-10: continue
@@ -146,6 +225,7 @@ if __name__ == "__main__":
         x1, x2, Ecv = f[name+"_x1"], f[name+"_x2"], f[name+"_E"]
         if not np.any(Ecv): print(name, "cv2 returned nothing"); continue
         E, mask, iters, log = find_essential_ransac(x1, x2, K)
+        if E is None: print(name, "no model"); continue
         d = min(np.abs(E - Ecv).max(), np.abs(E + Ecv).max())
         rm = f[name+"_ransac_mask"].ravel() if name+"_ransac_mask" in f else None
         print(f"{name}: n={len(x1)} iters={iters} inliers={int(mask.sum())} |E-Ecv|={d:.3e}", "mask_equal=%s" % (np.array_equal(mask, rm != 0) if rm is not None else "n/a"))

@@ -208,11 +208,23 @@ int vo_triangulate(vo_ctx* ctx, const float K[9], const float T1[12], const floa
                    const float* x1, const float* x2, int64_t n, float* xyz_out);
 int vo_triangulate_dev(vo_ctx* ctx, const float K[9], const float T1[12], const float T2[12],
                        const float* d_x1, const float* d_x2, int64_t n, float* d_xyz_out);
-/* Cam::computeEssentialAndRecoverPose (src/cam.cpp:37-91): essential matrix from matched pixel
- * pairs + OpenCV recoverPose (4 candidates, cheirality vote, |t| = 1, x2 = R x1 + t).
- * E,R,t are double (CV_64F in the reference); mask (nullable) = recoverPose's mask (0/255). */
+/* Cam::computeEssentialAndRecoverPose (src/cam.cpp:37-91): cv::findEssentialMat(p1, p2, K, cv::RANSAC) with
+ * OpenCV's defaults (five-point minimal solver inside RANSAC, confidence 0.999, threshold 1 px, <= 1000 iterations,
+ * no refit - restated incl. OpenCV's sampling sequence, null-space basis and root order, so the SAME hypothesis
+ * wins) followed by OpenCV's recoverPose (4 candidates, cheirality vote, |t| = 1, x2 = R x1 + t).
+ * E,R,t are double (CV_64F in the reference); mask (nullable) = recoverPose's mask (0/255).
+ * Fails with VO_ERR_STATE when no hypothesis reaches 5 inliers (the reference exits, cam.cpp:56-59). */
 int vo_essential_recover(vo_ctx* ctx, const float K[9], const float* x1, const float* x2, int64_t n,
                          double E[9], double R[9], double t[3], uint8_t* mask, int* n_good);
+/* The same with the estimator and its parameters explicit.  VO_ESSENTIAL_LINEAR8 is the batched alternative named
+ * by north_star: the normalised 8-point estimator on ALL matches (no outlier rejection; what vo_seq_batch_run uses).
+ * ransac_mask (nullable, 0/1), ransac_inliers, ransac_iters (nullable): findEssentialMat's mask output, the inlier
+ * count of the winning hypothesis and the number of samples OpenCV's loop would have consumed. */
+#define VO_ESSENTIAL_RANSAC5 0
+#define VO_ESSENTIAL_LINEAR8 1
+int vo_essential_recover_ex(vo_ctx* ctx, const float K[9], const float* x1, const float* x2, int64_t n, int method,
+                            double prob, double threshold, int max_iters, double E[9], double R[9], double t[3],
+                            uint8_t* mask, int* n_good, uint8_t* ransac_mask, int* ransac_inliers, int* ransac_iters);
 
 /* add_new_world_points (src/my_utilities.cpp:413-434): keep[j] = 1 iff cand_id[j] is not in
  * matched_id[0..n_matched). */

@@ -20,7 +20,7 @@ u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
 
 
 def build(force=False):
-    src = [os.path.join(_HERE, n) for n in ("vo_oracle.cpp", "vo_oracle.h")]
+    src = [os.path.join(_HERE, n) for n in ("vo_oracle.cpp", "five_point.cpp", "vo_oracle.h")]
     if (not force and os.path.exists(_SO)
             and all(os.path.getmtime(_SO) >= os.path.getmtime(s) for s in src)):
         return _SO
@@ -69,6 +69,15 @@ def lib():
     L.vo_ref_triangulate.restype = None
     L.vo_ref_essential_recover.argtypes = [f32p, f32p, f32p, C.c_int64, f64p, f64p, f64p, u8p]
     L.vo_ref_essential_recover.restype = C.c_int
+    L.vo_ref_find_essential_ransac.argtypes = [f32p, f32p, f32p, C.c_int64, C.c_double, C.c_double, C.c_int, f64p, C.c_void_p,
+                                               C.POINTER(C.c_int)]
+    L.vo_ref_find_essential_ransac.restype = C.c_int
+    L.vo_ref_essential_recover_ransac.argtypes = [f32p, f32p, f32p, C.c_int64, f64p, f64p, f64p, u8p]
+    L.vo_ref_essential_recover_ransac.restype = C.c_int
+    L.vo_ref_five_point.argtypes = [f64p, f64p, f64p]
+    L.vo_ref_five_point.restype = C.c_int
+    L.vo_ref_ransac_subsets.argtypes = [C.c_int, C.c_int, i32p]
+    L.vo_ref_ransac_subsets.restype = None
     L.vo_ref_recover_pose.argtypes = [f64p, f32p, f32p, f32p, C.c_int64, f64p, f64p, u8p]
     L.vo_ref_recover_pose.restype = C.c_int
     L.vo_ref_anti_join.argtypes = [i32p, C.c_int64, i32p, C.c_int64, u8p]
@@ -193,15 +202,44 @@ def triangulate(K, T1, T2, x1, x2):
     return out
 
 
-def essential_recover(K, x1, x2):
+def essential_recover(K, x1, x2, method="ransac"):
+    """src/cam.cpp:37-91. method "ransac": cv::findEssentialMat(RANSAC) restated (what the reference runs);
+    "8pt": the normalised linear estimator on all matches (the batched-sequence option)."""
     x1 = _f32(x1).reshape(-1, 2)
     x2 = _f32(x2).reshape(-1, 2)
     E = np.zeros(9)
     R = np.zeros(9)
     t = np.zeros(3)
     mask = np.zeros(max(len(x1), 1), np.uint8)
-    good = lib().vo_ref_essential_recover(_f32(K).ravel(), x1, x2, len(x1), E, R, t, mask)
+    fn = lib().vo_ref_essential_recover_ransac if method == "ransac" else lib().vo_ref_essential_recover
+    good = fn(_f32(K).ravel(), x1, x2, len(x1), E, R, t, mask)
     return E.reshape(3, 3), R.reshape(3, 3), t, mask[: len(x1)], good
+
+
+def find_essential_ransac(K, x1, x2, prob=0.999, threshold=1.0, max_iters=1000):
+    """cv::findEssentialMat(x1, x2, K, RANSAC, prob, threshold, maxIters) restated -> (E, mask, good, iterations)"""
+    x1 = _f32(x1).reshape(-1, 2)
+    x2 = _f32(x2).reshape(-1, 2)
+    E = np.zeros(9)
+    mask = np.zeros(max(len(x1), 1), np.uint8)
+    iters = C.c_int(0)
+    good = lib().vo_ref_find_essential_ransac(_f32(K).ravel(), x1, x2, len(x1), prob, threshold, max_iters, E,
+                                              mask.ctypes.data_as(C.c_void_p), C.byref(iters))
+    return E.reshape(3, 3), mask[: len(x1)], good, iters.value
+
+
+def five_point(q1, q2):
+    q1 = np.ascontiguousarray(q1, np.float64).reshape(10)
+    q2 = np.ascontiguousarray(q2, np.float64).reshape(10)
+    out = np.zeros(90)
+    n = lib().vo_ref_five_point(q1, q2, out)
+    return out[: 9 * n].reshape(n, 3, 3)
+
+
+def ransac_subsets(n, n_subsets):
+    out = np.zeros((n_subsets, 5), np.int32)
+    lib().vo_ref_ransac_subsets(int(n), int(n_subsets), out)
+    return out
 
 
 def recover_pose(E, K, x1, x2):

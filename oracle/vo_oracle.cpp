@@ -337,10 +337,8 @@ int recover_pose(const double E[9], const float K[9], const float* x1, const flo
                  double R[9], double t[3], uint8_t* mask_out) {
   const double fx = K[0], fy = K[4], cx = K[2], cy = K[5];
   const double dist_thr = 50.0;
-  double U[9], w[3], V[9], Vt[9];
-  svd3(E, U, w, V);
-  for (int i = 0; i < 3; ++i)
-    for (int j = 0; j < 3; ++j) Vt[3 * i + j] = V[3 * j + i];
+  double U[9], w[3], Vt[9];
+  vo_ref_cv_svd3(E, U, w, Vt);  // decomposeEssentialMat: SVD::compute(E, D, U, Vt) with OpenCV's own Jacobi SVD
   if (det3(U) < 0)
     for (double& v : U) v = -v;
   if (det3(Vt) < 0)
@@ -650,6 +648,8 @@ void vo_ref_triangulate(const float K[9], const float T1[12], const float T2[12]
     xyz_out[3 * i + 2] = Xf[2] * scale;
   }
 }
+
+void vo_ref_jacobi_svd(double* A, int m, int n, double* V, double* w) { jacobi_svd(A, m, n, V, w); }
 
 int vo_ref_recover_pose(const double E[9], const float K[9], const float* x1, const float* x2, int64_t n,
                         double R[9], double t[3], uint8_t* mask) {

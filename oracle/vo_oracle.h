@@ -99,6 +99,24 @@ void vo_ref_triangulate(const float K[9], const float T1[12], const float T2[12]
 int vo_ref_essential_recover(const float K[9], const float* x1, const float* x2, int64_t n,
                              double E[9], double R[9], double t[3], uint8_t* mask);
 
+/* src/cam.cpp:49 AS THE REFERENCE RUNS IT: cv::findEssentialMat(p1, p2, K, RANSAC) restated (five_point.cpp:
+ * OpenCV's RNG, subset selection, 5-point solver incl. its null-space basis and root order, Sampson inliers, adaptive
+ * iteration count; no refit).  Returns the inlier count of the winning hypothesis (0: none). mask (nullable) 0/1. */
+int vo_ref_find_essential_ransac(const float K[9], const float* x1, const float* x2, int64_t n, double prob,
+                                 double threshold, int max_iters, double E[9], uint8_t* mask, int* iters_out);
+/* ... followed by recoverPose (src/cam.cpp:61): the reference's computeEssentialAndRecoverPose */
+int vo_ref_essential_recover_ransac(const float K[9], const float* x1, const float* x2, int64_t n, double E[9],
+                                    double R[9], double t[3], uint8_t* mask);
+/* EMEstimatorCallback::runKernel: 5 normalised correspondences (x,y interleaved) -> up to 10 E (row-major, unit norm) */
+int vo_ref_five_point(const double q1[10], const double q2[10], double E_out[90]);
+/* the first n_subsets 5-subsets RANSACPointSetRegistrator::getSubset draws for a set of n points */
+void vo_ref_ransac_subsets(int n, int n_subsets, int32_t* idx_out);
+/* cv::SVD::compute of a 3x3 matrix restated (OpenCV's JacobiSVDImpl_: its rotation order fixes the signs of the
+ * singular vectors, which decide the candidate ORDER in recoverPose when cheirality votes tie) */
+void vo_ref_cv_svd3(const double A[9], double U[9], double w[3], double Vt[9]);
+/* one-sided Jacobi SVD (A m x n row-major -> U*Sigma in place, V n x n, w descending) */
+void vo_ref_jacobi_svd(double* A, int m, int n, double* V, double* w);
+
 /* OpenCV recoverPose alone, for pinning against cv2 with a given E */
 int vo_ref_recover_pose(const double E[9], const float K[9], const float* x1, const float* x2,
                         int64_t n, double R[9], double t[3], uint8_t* mask);

@@ -20,7 +20,7 @@ def product():
 class OracleBackend:
     name = "oracle"
 
-    def __init__(self, essential="8pt", cv2_first_pose=None):
+    def __init__(self, essential="ransac", cv2_first_pose=None):
         self.essential = essential
         self.cv2_first_pose = cv2_first_pose
 
@@ -33,7 +33,7 @@ class OracleBackend:
         if self.cv2_first_pose is not None:  # anchor run: cv2's own (R, t) from the fixtures
             R, t, mask = self.cv2_first_pose
             return R, t, mask
-        E, R, t, mask, good = O.essential_recover(K, x1, x2)
+        E, R, t, mask, good = O.essential_recover(K, x1, x2, method=self.essential)
         return R, t, mask
 
     def triangulate(self, K, T1, T2, x1, x2):
@@ -65,9 +65,10 @@ class GpuBackend:
     """Every numeric step goes through libvo_b200.so (host buffers in, host buffers out)."""
     name = "gpu"
 
-    def __init__(self, ctx=None):
+    def __init__(self, ctx=None, essential="ransac"):
         self.vo = product()
         self.ctx = ctx or self.vo.Context(0)
+        self.essential = essential
 
     def match(self, dA, dB, idA=None, idB=None):
         if len(dA) == 0 or len(dB) == 0:
@@ -75,7 +76,7 @@ class GpuBackend:
         return self.ctx.match(dA, dB, 0.2, 0.8, idA, idB)
 
     def essential_recover(self, K, x1, x2):
-        E, R, t, mask, good = self.ctx.essential_recover(K, x1, x2)
+        E, R, t, mask, good = self.ctx.essential_recover(K, x1, x2, method=self.essential)
         return R, t, mask
 
     def triangulate(self, K, T1, T2, x1, x2):

@@ -48,7 +48,7 @@ def test_bundled_dataset_as_a_batch_of_one(ctx, dataset):
         n = len(fr["uv"])
         uv[0, f, :n], desc[0, f, :n], ids[0, f, :n] = fr["uv"], fr["desc"], fr["id_real"]
     out = ctx.seq_batch_run(vo.seq_params(replay.K_REF), cnt, uv, desc, ids)
-    ref = replay.run_icp_test(dataset, backends.OracleBackend())
+    ref = replay.run_icp_test(dataset, backends.OracleBackend(essential="8pt"))
     _compare(out, 0, ref, F)
     assert out["world_cnt"][0] == 490
     ev = replay.evaluate(dataset, dict(poses=out["poses"][0], world=ref["world"]))
@@ -65,7 +65,7 @@ def test_synthetic_batch_matches_oracle_replay(ctx):
     assert (out["status"] == 0).all()
     for s in (0, 5, 11, 23):
         ds = simulator.as_dataset(batch, s)
-        ref = replay.run_icp_test(ds, backends.OracleBackend(), n_meas=F)
+        ref = replay.run_icp_test(ds, backends.OracleBackend(essential="8pt"), n_meas=F)
         _compare(out, s, ref, F)
     # independent sequences: a sequence's result does not depend on its neighbours in the batch
     solo = ctx.seq_batch_run(vo.seq_params(replay.K_REF), batch["cnt"][5:6], batch["uv"][5:6], batch["desc"][5:6],
