@@ -294,6 +294,36 @@ __device__ void picp_solve_update(const double* __restrict__ res, float damping,
   }
 }
 
+// lane `lane` reads term `lane` of every rank out of THIS GPU's mailbox (parity buffer `par`) until all words carry
+// sequence number `seq`, and adds the ranks' doubles in rank order.  false: gave up after ~5 s (a peer never came).
+__device__ __forceinline__ bool peer_collect(VoMailbox* me, int par, unsigned seq, int peer_n, int lane, double& total) {
+  unsigned long long r0[VO_MAX_PEERS], r1[VO_MAX_PEERS];
+  bool ok = false;
+  for (long long spins = 0; spins < (1ll << 23); ++spins) {
+    bool all = true;
+#pragma unroll
+    for (int q = 0; q < VO_MAX_PEERS; ++q) {
+      if (q < peer_n) {
+        const volatile unsigned long long* src = &me->ll[par][q][lane][0];
+        r0[q] = src[0];
+        r1[q] = src[1];
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < VO_MAX_PEERS; ++q)
+      if (q < peer_n) all = all && ((unsigned)(r0[q] >> 32) == seq) && ((unsigned)(r1[q] >> 32) == seq);
+    if (all) {
+      ok = true;
+      break;
+    }
+  }
+  total = 0.0;
+#pragma unroll
+  for (int q = 0; q < VO_MAX_PEERS; ++q)
+    if (q < peer_n) total += __longlong_as_double((long long)((r0[q] & 0xffffffffull) | (r1[q] << 32)));
+  return ok;
+}
+
 // ------------------------------------------------------------------ fused all-reduce over NVLink peer memory
 // One warp. Lane c owns term c. Push my 32 terms into every rank's mailbox (mine included) as self-validating
 // 8-byte words {half of the double | sequence number}, poll my own mailbox until every rank's words carry this
@@ -313,27 +343,14 @@ __device__ __forceinline__ double picp_peer_allreduce(const LinArgs& a, double m
     dst[0] = w0;
     dst[1] = w1;
   }
-  // lane c collects term c of every rank in RANK order as the words arrive
+  // lane c collects term c of every rank: all 2 x n loads in flight at once (one L2 round trip per poll, not one per
+  // rank), repeated until every word carries this round's number; the sum then runs in RANK order
   double total = 0.0;
-  bool ok = true;
-  for (int q = 0; q < a.peer_n; ++q) {
-    const volatile unsigned long long* src = &me->ll[par][q][lane][0];
-    unsigned long long r0 = src[0], r1 = src[1];
-    long long spins = 0;
-    while ((unsigned)(r0 >> 32) != seq || (unsigned)(r1 >> 32) != seq) {
-      if (++spins > (1ll << 24)) {  // ~5 s: a peer never launched its round; flag it instead of hanging the GPU
-        ok = false;
-        break;
-      }
-      r0 = src[0];
-      r1 = src[1];
-    }
-    total += __longlong_as_double((long long)((r0 & 0xffffffffull) | (r1 << 32)));
-  }
-  ok = __all_sync(0xffffffffu, ok);
+  const bool ok = peer_collect(me, par, seq, a.peer_n, lane, total);
+  const bool all_ok = __all_sync(0xffffffffu, ok);
   if (lane == 0) {
     *(volatile unsigned*)&me->seq = seq;
-    if (!ok) me->timeout = 1u;
+    if (!all_ok) me->timeout = 1u;
   }
   return total;
 }
@@ -766,21 +783,7 @@ __global__ void __launch_bounds__(kResThreads, 1) picp_resident_kernel(const Res
           }
         }
         // every CTA: term `lane` of every rank out of this GPU's mailbox, added in RANK order
-        tot = 0.0;
-        for (int q = 0; q < a.peer_n; ++q) {
-          const volatile unsigned long long* src = &me->ll[par][q][lane][0];
-          unsigned long long r0 = src[0], r1 = src[1];
-          long long spins = 0;
-          while ((unsigned)(r0 >> 32) != mseq || (unsigned)(r1 >> 32) != mseq) {
-            if (++spins > (1ll << 23)) {
-              ok = false;
-              break;
-            }
-            r0 = src[0];
-            r1 = src[1];
-          }
-          tot += __longlong_as_double((long long)((r0 & 0xffffffffull) | (r1 << 32)));
-        }
+        ok = peer_collect(me, par, mseq, a.peer_n, lane, tot);
         ok = __all_sync(0xffffffffu, ok);
       }
       s_tot[lane] = tot;

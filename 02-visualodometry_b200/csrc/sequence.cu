@@ -451,31 +451,30 @@ int vo_seq_batch_run(vo_ctx* ctx, const vo_seq_params* params, int n_seq, int n_
   VO_REQUIRE(ctx, n_seq >= 0 && n_frames >= 1 && max_pts >= 1 && world_cap >= 1, "vo_seq_batch_run: sizes");
   if (n_seq == 0) return VO_OK;
   const size_t SF = (size_t)n_seq * n_frames, SFP = SF * max_pts, SW = (size_t)n_seq * world_cap;
-  const size_t bytes[] = {SF * 4, SFP * 8, SFP * kDim * 4, SFP * 4, SF * 48, SW * 12, SW * 4, (size_t)n_seq * 4, SF * 4, SF * 8, (size_t)n_seq * 4};
-  void* d[11] = {nullptr};
-  cudaError_t e = cudaSuccess;
-  for (int i = 0; i < 11 && e == cudaSuccess; ++i) e = cudaMalloc(&d[i], bytes[i]);
-  auto cleanup = [&]() {
-    for (int i = 0; i < 11; ++i)
-      if (d[i]) cudaFree(d[i]);
-  };
-  if (e != cudaSuccess) {
-    cleanup();
-    return vo_set_error(ctx, VO_ERR_NOMEM, "vo_seq_batch_run: cudaMalloc", cudaGetErrorString(e));
-  }
+  const size_t bytes[11] = {SF * 4, SFP * 8, SFP * kDim * 4, SFP * 4, SF * 48, SW * 12, SW * 4, (size_t)n_seq * 4, SF * 4, SF * 8, (size_t)n_seq * 4};
+  // one staging arena per context (grown on demand, reused): no cudaMalloc / cudaFree per call.  Inputs first, then
+  // the outputs as ONE block that is zeroed before the launch: a sequence that stops early (status 2 / 3) hands
+  // zeros, not stale device memory, back to the caller.
+  size_t off[12];
+  off[0] = 0;
+  for (int i = 0; i < 11; ++i) off[i + 1] = vo_align_up(off[i] + bytes[i], 256);
+  char* base;
+  st = vo_stage(ctx, off[11], (void**)&base);
+  if (st) return st;
+  void* d[11];
+  for (int i = 0; i < 11; ++i) d[i] = base + off[i];
+  VO_CUDA(ctx, cudaMemsetAsync(d[4], 0, off[11] - off[4], ctx->stream));
   const void* src[4] = {cnt, uv, desc, id_real};
-  for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaMemcpyAsync(d[i], src[i], bytes[i], cudaMemcpyHostToDevice, ctx->stream);
-  if (e == cudaSuccess)
-    st = vo_seq_batch_run_dev(ctx, params, n_seq, n_frames, max_pts, world_cap, (int32_t*)d[0], (float*)d[1], (float*)d[2],
-                              (int32_t*)d[3], (float*)d[4], (float*)d[5], (int32_t*)d[6], (int32_t*)d[7], (int32_t*)d[8],
-                              (int32_t*)d[9], (int32_t*)d[10]);
+  for (int i = 0; i < 4; ++i) VO_CUDA(ctx, cudaMemcpyAsync(d[i], src[i], bytes[i], cudaMemcpyHostToDevice, ctx->stream));
+  st = vo_seq_batch_run_dev(ctx, params, n_seq, n_frames, max_pts, world_cap, (int32_t*)d[0], (float*)d[1], (float*)d[2],
+                            (int32_t*)d[3], (float*)d[4], (float*)d[5], (int32_t*)d[6], (int32_t*)d[7], (int32_t*)d[8],
+                            (int32_t*)d[9], (int32_t*)d[10]);
+  if (st) return st;
   void* dst[7] = {poses, world_xyz, world_id, world_cnt, rounds, inliers, status};
-  for (int i = 0; i < 7 && e == cudaSuccess && st == VO_OK; ++i)
-    if (dst[i]) e = cudaMemcpyAsync(dst[i], d[4 + i], bytes[4 + i], cudaMemcpyDeviceToHost, ctx->stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-  cleanup();
-  if (e != cudaSuccess) return vo_set_error(ctx, VO_ERR_CUDA, "vo_seq_batch_run", cudaGetErrorString(e));
-  return st;
+  for (int i = 0; i < 7; ++i)
+    if (dst[i]) VO_CUDA(ctx, cudaMemcpyAsync(dst[i], d[4 + i], bytes[4 + i], cudaMemcpyDeviceToHost, ctx->stream));
+  VO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return VO_OK;
 }
 
 }  // extern "C"

@@ -97,10 +97,23 @@ const Camera& PICPSolver::camera() const {
   return camera_;
 }
 
-static uint64_t fnv1a(const void* data, size_t bytes) {
-  const unsigned char* p = (const unsigned char*)data;
+// Fingerprint of a correspondence vector: the whole of a small one, a bounded sample of a large one (head, tail and
+// 4096 evenly spaced pairs) - at 10 M correspondences hashing all 80 MB on one core would cost more per round than the
+// Gauss-Newton round itself.  A caller that rewrites a few pairs in the middle of a large vector in place, at the same
+// address and size, must call init() again (the reference's drivers build a fresh vector per frame).
+static uint64_t corr_fingerprint(const void* data, size_t n_pairs) {
+  const uint64_t* p = (const uint64_t*)data;  // one IntPair = 8 bytes
   uint64_t h = 1469598103934665603ull;
-  for (size_t i = 0; i < bytes; ++i) h = (h ^ p[i]) * 1099511628211ull;
+  auto mix = [&](uint64_t v) { h = (h ^ v) * 1099511628211ull; h ^= h >> 29; };
+  const size_t full = 8192;
+  if (n_pairs <= full) {
+    for (size_t i = 0; i < n_pairs; ++i) mix(p[i]);
+    return h;
+  }
+  for (size_t i = 0; i < 2048; ++i) mix(p[i]);
+  for (size_t i = n_pairs - 2048; i < n_pairs; ++i) mix(p[i]);
+  const size_t step = n_pairs / 4096;
+  for (size_t i = 0; i < n_pairs; i += step) mix(p[i]);
   return h;
 }
 
@@ -108,7 +121,7 @@ bool PICPSolver::oneRound(const IntPairVector& correspondences, bool keep_outlie
   if (!h_) throw std::runtime_error("PICPSolver::oneRound before init");
   // the caller hands the same vector every iteration (exec/icp_test.cpp:94-107): upload + gather once
   const void* ptr = correspondences.empty() ? nullptr : (const void*)&correspondences[0];
-  const uint64_t hash = fnv1a(ptr, correspondences.size() * sizeof(IntPair));
+  const uint64_t hash = corr_fingerprint(ptr, correspondences.size());
   if (ptr != corr_ptr_ || correspondences.size() != corr_size_ || hash != corr_hash_ || corr_ptr_ == nullptr) {
     vo::check(vo_picp_set_correspondences(h_->p, (const int32_t*)ptr, (int64_t)correspondences.size()),
               "vo_picp_set_correspondences");

@@ -37,6 +37,12 @@ def cv2pose():
 
 
 @pytest.fixture(scope="session")
+def world_gt():
+    """data/world.dat + the camera-in-robot transform of data/camera.dat (oracle/gen_golden_world.py)"""
+    return np.load(os.path.join(ROOT, "tests", "golden", "world_gt.npz"))
+
+
+@pytest.fixture(scope="session")
 def oracle():
     from oracle import pyoracle
     pyoracle.build()

@@ -173,3 +173,36 @@ def evaluate(ds, res):
         p = C @ w.xyz[k].astype(np.float64) * scale
         rows.append([rid, p[0], p[1], p[2]])
     return dict(scale=scale, traj=traj, traj_scaled=traj_s, errors=err, world_points=np.array(rows))
+
+
+def _robot_T(p):
+    x, y, th = p
+    T = np.eye(4)
+    T[:2, :2] = [[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]]
+    T[0, 3], T[1, 3] = x, y
+    return T
+
+
+def triangulation_kat(be, dataset, world_gt):
+    """exec/triangulate_points_test.cpp:33-72 as a known-answer test: frames 0/1 -> match -> essential + recoverPose ->
+    triangulate, against data/world.dat[id_real] moved into camera 0 (ground-truth robot pose x camera-in-robot of
+    data/camera.dat).  The reconstruction is in units of the baseline (|t| = 1): the least-squares scale must be the
+    true baseline 0.2004 and every landmark within 0.5 % of its distance (measured: median 3.6e-4, max 2.3e-3; the
+    pixels carry 1e-2 px print-precision noise)."""
+    f0, f1 = frame(dataset, 0), frame(dataset, 1)
+    m, _ = be.match(f0["desc"], f1["desc"], f0["id_real"], f1["id_real"])
+    x1, x2 = f0["uv"][m[:, 0]], f1["uv"][m[:, 1]]
+    R, t, mask = be.essential_recover(K_REF, x1, x2)
+    assert len(m) == 115 and int((np.asarray(mask) != 0).sum()) == 115
+    T = np.concatenate([np.asarray(R, np.float32), np.asarray(t, np.float32).reshape(3, 1)], 1)
+    X = be.triangulate(K_REF, I34, be.pose_inverse(T), x1, x2).astype(np.float64)
+    ids = f0["id_real"][m[:, 0]]
+    C0 = _robot_T(dataset["gt_pose"][0]) @ world_gt["cam_in_robot"]
+    C1 = _robot_T(dataset["gt_pose"][1]) @ world_gt["cam_in_robot"]
+    Xw = np.concatenate([world_gt["xyz"][ids], np.ones((len(ids), 1))], 1)
+    Xc = (np.linalg.inv(C0) @ Xw.T).T[:, :3]
+    base = np.linalg.norm(C1[:3, 3] - C0[:3, 3])
+    scale = (X * Xc).sum() / (X * X).sum()
+    assert abs(scale - base) <= 1e-3 * base, (scale, base)
+    err = np.linalg.norm(X * base - Xc, axis=1) / np.linalg.norm(Xc, axis=1)
+    assert err.max() <= 5e-3 and np.median(err) <= 1e-3, (err.max(), np.median(err))

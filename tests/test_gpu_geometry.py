@@ -124,6 +124,28 @@ def test_ransac_essential_edge_cases(ctx, oracle):
         assert "no essential matrix" in str(e)
 
 
+def test_triangulation_kat_vs_world_dat(ctx, dataset, world_gt):
+    """the GPU path (match -> RANSAC essential -> recoverPose -> DLT) against the simulator's ground truth landmarks"""
+    import backends
+    import replay
+    replay.triangulation_kat(backends.GpuBackend(ctx), dataset, world_gt)
+
+
+def test_essential_inlier_kat(ctx, dataset):
+    """exec/pose_recovery_test.cpp:29-62 on the GPU: every match of a consecutive frame pair is a RANSAC inlier"""
+    import replay
+    for i in range(0, 120, 7):
+        a, b = replay.frame(dataset, i), replay.frame(dataset, i + 1)
+        m, _ = ctx.match(a["desc"], b["desc"], 0.2, 0.8)
+        if len(m) < 8:
+            continue
+        x1, x2 = a["uv"][m[:, 0]], b["uv"][m[:, 1]]
+        E, R, t, mask, good, rmask, rin, rit = ctx.essential_recover(replay.K_REF, x1, x2, full=True)
+        assert rin == len(m) and rmask.all() and rit <= 2, i
+        if i <= 50:
+            assert good == len(m), i
+
+
 @pytest.mark.parametrize("keep", [False, True])
 def test_project_points(ctx, oracle, keep):
     fr = synth.picp_frame(n=10000, seed=2)

@@ -136,3 +136,47 @@ def test_native_icp_test_reproduces_output(dataset, tmp_path):
     py = replay.evaluate(dataset, replay.run_icp_test(dataset, backends.GpuBackend()))
     assert np.abs(got["traj"][:, 1:3] - py["traj"][:, 1:3]).max() <= 2e-3
     assert abs(got["traj_scaled"][1, 1] / got["traj"][1, 1] - py["scale"]) <= 1e-4
+
+
+ONE_ROUND_BIN = os.path.join(ROOT, "02-visualodometry_b200", "host", "one_round_native")
+
+
+def _run_free_one_round(tmp_path, pose, world, image, pairs):
+    inp, out = tmp_path / "in.bin", tmp_path / "out.bin"
+    with open(inp, "wb") as f:
+        f.write(np.array([len(world), len(image), len(pairs)], np.int32).tobytes())
+        f.write(np.ascontiguousarray(pose, np.float32).tobytes())
+        f.write(np.ascontiguousarray(world, np.float32).tobytes())
+        f.write(np.ascontiguousarray(image, np.float32).tobytes())
+        f.write(np.ascontiguousarray(pairs, np.int32).tobytes())
+    r = subprocess.run([ONE_ROUND_BIN, str(inp), str(out)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return np.fromfile(out, np.float32).reshape(3, 4), r
+
+
+@pytest.mark.gpu
+def test_free_one_round_driver(tmp_path, oracle):
+    """The third driver of the solver, the free oneRound() (src/my_utilities.cpp:263-315), through the host mirror:
+    kernel threshold 100 with outliers KEPT (the lambda = sqrt(thr/chi) branch, src/picp_solver.cpp:77-80), <= 50
+    rounds, stop at the first round whose relative chi_inliers change is below 5 %; against the same loop on the
+    oracle.  Fewer than 10 correspondences: the input pose comes back untouched (:269-273)."""
+    import synth
+    fr = synth.picp_frame(n=4000, seed=31, permute=True)
+    pose, r = _run_free_one_round(tmp_path, fr["pose0"], fr["world"], fr["image"], fr["pairs"])
+    ref = fr["pose0"].copy()
+    prev, rounds = np.finfo(np.float64).max, 0
+    for i in range(50):
+        ref, ci, co, ni = oracle.one_round(fr["K"], 480, 640, ref, fr["world"], fr["image"], fr["pairs"], 100.0, 1.0, True)
+        rounds += 1
+        rel = abs(prev - float(ci)) / prev if prev > 1e-10 else 0.0
+        if rel < 0.05:
+            break
+        prev = float(ci)
+    assert np.abs(pose - ref).max() <= 1e-5
+    assert "Kernel threshold set to 100.0f" in r.stdout
+    assert f"Convergence reached at iteration {rounds - 1}" in r.stdout
+    assert np.abs(pose - fr["pose_gt"]).max() < np.abs(fr["pose0"] - fr["pose_gt"]).max()  # it did move towards GT
+    # < 10 correspondences: early return of the input pose, bit for bit
+    pose9, r9 = _run_free_one_round(tmp_path, fr["pose0"], fr["world"], fr["image"], fr["pairs"][:9])
+    assert np.array_equal(pose9, fr["pose0"])
+    assert "Not enough correspondences" in r9.stderr

@@ -118,6 +118,27 @@ def test_ransac_building_blocks(oracle, cv2fx):
         assert np.abs(((b @ E) * a).sum(1)).max() < 1e-12
 
 
+def test_triangulation_kat_vs_world_dat(oracle, dataset, world_gt):
+    replay.triangulation_kat(backends.OracleBackend(), dataset, world_gt)
+
+
+def test_essential_inlier_kat(oracle, dataset):
+    """exec/pose_recovery_test.cpp:29-62 as a known-answer test: on the noise-free dataset EVERY match of every
+    consecutive frame pair is a RANSAC inlier of the winning hypothesis (1 px threshold), and wherever the robot
+    translates (frames 0..50) every match also passes recoverPose's cheirality vote (where it turns on the spot the
+    50-baseline distance cap of recoverPose drops far points, as in OpenCV)."""
+    for i in range(0, 120, 3):
+        a, b = replay.frame(dataset, i), replay.frame(dataset, i + 1)
+        m, _ = oracle.match(a["desc"], b["desc"], 0.2, 0.8)
+        if len(m) < 8:
+            continue
+        x1, x2 = a["uv"][m[:, 0]], b["uv"][m[:, 1]]
+        E, rmask, rgood, iters = oracle.find_essential_ransac(replay.K_REF, x1, x2)
+        assert rgood == len(m) and rmask.all() and iters <= 2, i
+        if i <= 50:
+            assert oracle.essential_recover(replay.K_REF, x1, x2)[4] == len(m), i
+
+
 def test_matching_kat_ids(oracle, dataset):
     """exec/match_points_test.cpp:20-39 as a KAT: on data/ every accepted pair has equal id_real,
     and every id present in both frames is found (descriptors are exact copies)."""
