@@ -101,6 +101,9 @@ _sig("vo_match", C.c_int, _vp, _vp, _i64, _vp, _i64, C.c_int, _f, _f, _vp, _vp, 
      C.POINTER(_i64), _vp)
 _sig("vo_match_dev", C.c_int, _vp, _vp, _i64, _vp, _i64, C.c_int, _f, _f, _vp, _vp, _i64, _i64, _vp, _i64,
      C.POINTER(_i64), _vp, _vp, _vp, _vp)
+_sig("vo_match_sharded_dev", C.c_int, _vp, _vp, _i64, _vp, _i64, C.c_int, _f, _f, C.c_int, C.c_int, _vp, _vp, _i64,
+     C.POINTER(_i64))
+_sig("vo_match_compact_dev", C.c_int, _vp, _vp, _i64, _vp, _i64, C.POINTER(_i64))
 _sig("vo_match_set_path", C.c_int, _vp, C.c_int)
 _sig("vo_selftest_reciprocal", C.c_int, _vp, _vp)
 _sig("vo_triangulate", C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp)
@@ -291,6 +294,22 @@ class Context:
                                     C.byref(n_out), _p(stats), _p(d_best), _p(d_second), _p(d_idx)),
                     "vo_match_dev")
         return n_out.value, (int(stats[0]), int(stats[1]))
+
+    def match_sharded_dev(self, d_descA, n1, d_descB, n2, dim, shard, n_shards, d_match_idx, d_pairs_out=None, capacity=0,
+                          dist_thr=0.2, ratio_thr=0.8):
+        """this shard's share of all n1 rows (Morton-order segments on the indexed path), the MAX all-reduce of the
+        per-row results when a communicator is attached, and the compacted pairs; returns the pair count"""
+        n_out = _i64(0)
+        self._check(_L.vo_match_sharded_dev(self._h, _p(d_descA), n1, _p(d_descB), n2, dim, dist_thr, ratio_thr, shard,
+                                            n_shards, _p(d_match_idx), _p(d_pairs_out), capacity, C.byref(n_out)),
+                    "vo_match_sharded_dev")
+        return n_out.value
+
+    def match_compact_dev(self, d_match_idx, n1, d_pairs_out, capacity):
+        n_out = _i64(0)
+        self._check(_L.vo_match_compact_dev(self._h, _p(d_match_idx), n1, _p(d_pairs_out), capacity, C.byref(n_out)),
+                    "vo_match_compact_dev")
+        return n_out.value
 
     # ---- Cam
     def triangulate(self, K, T1, T2, x1, x2):

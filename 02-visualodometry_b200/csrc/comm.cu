@@ -164,3 +164,12 @@ int vo_comm_allreduce_f64(vo_ctx* ctx, double* d_buf, int n) {
   if (r != 0) return vo_set_error(ctx, VO_ERR_NCCL, "ncclAllReduce", nccl_err(r));
   return VO_OK;
 }
+
+// element-wise MAX of n int32 in place over the communicator (the sharded matcher's exchange); no-op without one
+int vo_comm_allreduce_max_i32(vo_ctx* ctx, int32_t* d_buf, long long n) {
+  if (!ctx->nccl_comm) return VO_OK;
+  const int kNcclInt32 = 2, kNcclMax = 2;  // ncclInt32, ncclMax
+  int r = g_nccl.all_reduce(d_buf, d_buf, (size_t)n, kNcclInt32, kNcclMax, ctx->nccl_comm, ctx->stream);
+  if (r != 0) return vo_set_error(ctx, VO_ERR_NCCL, "ncclAllReduce", nccl_err(r));
+  return VO_OK;
+}

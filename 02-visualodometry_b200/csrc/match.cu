@@ -627,6 +627,9 @@ __device__ __forceinline__ float min3(float a, float b, float c) {  // FMNMX3; N
 #ifndef VO_MMA_BUFS
 #define VO_MMA_BUFS 1
 #endif
+#ifndef VO_MATCH_DENSE_GUARD
+#define VO_MATCH_DENSE_GUARD 1
+#endif
 constexpr int kDenseMinPerRow = 48;  // survivors of one row in a 128-column tile from which the outright scan is cheaper
 constexpr int kDenseSkip = 7;        // tiles evaluated outright after a dense one before the filter is tried again
 constexpr int kFragBufs = VO_MMA_BUFS;             // tile fragment buffers per warp (TMA bulk copies in flight)
@@ -824,7 +827,7 @@ __global__ void __launch_bounds__(VO_MMA_LB) match_scan10_mma_kernel(
         // exact twin's arithmetic - than survivor by survivor; and the tiles that follow such a tile skip the filter
         // altogether, re-probing every kDenseSkip tiles.  Exactness is unaffected: evaluating a column that the filter
         // would have excluded can change neither value nor index (update_best_tie is order independent).
-        bool dense = dense_skip > 0;
+        bool dense = VO_MATCH_DENSE_GUARD && dense_skip > 0;
         if (dense) --dense_skip;
         if (!dense)
 #pragma unroll
@@ -865,7 +868,7 @@ __global__ void __launch_bounds__(VO_MMA_LB) match_scan10_mma_kernel(
         if (!dense) {
           if (!__any_sync(0xffffffffu, mine)) continue;
           const int kept = __popc(mk.x) + __popc(mk.y) + __popc(mk.z) + __popc(mk.w);
-          if (__reduce_max_sync(0xffffffffu, kept) >= kDenseMinPerRow) {
+          if (VO_MATCH_DENSE_GUARD && __reduce_max_sync(0xffffffffu, kept) >= kDenseMinPerRow) {
             dense = true;
             dense_skip = kDenseSkip;
             if (mine) *reinterpret_cast<uint4*>(mask + lane * 4) = make_uint4(0, 0, 0, 0);
@@ -1141,12 +1144,33 @@ extern "C" int vo_debug_match_counters(unsigned long long out[4], int reset) {
 }
 #endif
 
-extern "C" {
+// per-row match index for the exchange of the sharded matcher: best column if the row was accepted, else -1
+__global__ void __launch_bounds__(256) match_idx_kernel(const unsigned char* __restrict__ flags, const int* __restrict__ idx,
+                                                        long long rows, int* __restrict__ out) {
+  const long long r = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (r < rows) out[r] = flags[r] ? idx[r] : -1;
+}
 
-int vo_match_dev(vo_ctx* ctx, const float* d_descA, int64_t n1, const float* d_descB, int64_t n2, int dim,
-                 float dist_thr, float ratio_thr, const int32_t* d_idA, const int32_t* d_idB, int64_t row_begin,
-                 int64_t row_end, int32_t* d_pairs_out, int64_t capacity, int64_t* n_out, int64_t stats[2],
-                 float* d_best, float* d_second, int32_t* d_best_idx) {
+// pairs (i, m[i]) for m[i] >= 0, ascending i: flags + per-block counts, then the shared scan / scatter
+__global__ void __launch_bounds__(256) match_idx_flags_kernel(const int* __restrict__ m, long long rows,
+                                                              unsigned char* __restrict__ flags, int* __restrict__ block_counts) {
+  const long long r = (long long)blockIdx.x * 256 + threadIdx.x;
+  const int acc = (r < rows) && (m[r] >= 0);
+  if (r < rows) flags[r] = (unsigned char)acc;
+  const int cnt = __syncthreads_count(acc);
+  if (threadIdx.x == 0) block_counts[blockIdx.x] = cnt;
+}
+
+// curve_shard / n_curve_shards: with n_curve_shards > 1 the call covers ALL rows [0, n1) but scans only this
+// shard's share of them: the shard-th contiguous segment of the rows' Morton order on the indexed path (every shard
+// then sees the row density of the unsharded problem, so the index prunes as well as on one GPU), a contiguous
+// index block otherwise.  Rows of other shards come out as "no match".  d_match_idx (nullable): per-row result
+// for the exchange between the shards (accepted ? best column : -1).
+int match_dev_impl(vo_ctx* ctx, const float* d_descA, int64_t n1, const float* d_descB, int64_t n2, int dim,
+                   float dist_thr, float ratio_thr, const int32_t* d_idA, const int32_t* d_idB, int64_t row_begin,
+                   int64_t row_end, int32_t* d_pairs_out, int64_t capacity, int64_t* n_out, int64_t stats[2],
+                   float* d_best, float* d_second, int32_t* d_best_idx, int curve_shard, int n_curve_shards,
+                   int32_t* d_match_idx) {
   if (!ctx) return VO_ERR_INVALID;
   int st = vo_ctx_activate(ctx);
   if (st) return st;
@@ -1161,6 +1185,23 @@ int vo_match_dev(vo_ctx* ctx, const float* d_descA, int64_t n1, const float* d_d
   VO_REQUIRE(ctx, rows < 0x7fffffffLL, "vo_match: at most 2^31-1 rows per call");
   VO_REQUIRE(ctx, d_descA && (n2 == 0 || d_descB), "vo_match: null descriptors");
   VO_REQUIRE(ctx, capacity == 0 || d_pairs_out, "vo_match: null pairs_out");
+  VO_REQUIRE(ctx, n_curve_shards >= 1 && curve_shard >= 0 && curve_shard < n_curve_shards, "vo_match: shard");
+  if (n_curve_shards > 1) {
+    const bool can_index = (dim == 10) && n2 >= kSortMinRows && ctx->match_path != VO_MATCH_PATH_BRUTE &&
+                           ctx->match_path != VO_MATCH_PATH_ORDERED &&
+                           (rows >= kIndexMinRows || (rows >= 32 && rows * n2 >= kIndexMinPairs));
+    if (!can_index) {  // no Morton order to shard along: this shard's contiguous block of row indices
+      const long long lo = row_begin + rows * curve_shard / n_curve_shards;
+      const long long hi = row_begin + rows * (curve_shard + 1) / n_curve_shards;
+      if (d_match_idx) VO_CUDA(ctx, cudaMemsetAsync(d_match_idx, 0xFF, (size_t)rows * 4, ctx->stream));
+      if (hi == lo) return VO_OK;
+      return match_dev_impl(ctx, d_descA, n1, d_descB, n2, dim, dist_thr, ratio_thr, d_idA, d_idB, lo, hi, d_pairs_out,
+                            capacity, n_out, stats, d_best ? d_best + (lo - row_begin) : nullptr,
+                            d_second ? d_second + (lo - row_begin) : nullptr,
+                            d_best_idx ? d_best_idx + (lo - row_begin) : nullptr, 0, 1,
+                            d_match_idx ? d_match_idx + (lo - row_begin) : nullptr);
+    }
+  }
 
   // column splits: fill whole waves (sm_count * resident CTAs) without starving any CTA of work
   const long long row_blocks = (rows + kMatchThreads - 1) / kMatchThreads;
@@ -1280,8 +1321,12 @@ int vo_match_dev(vo_ctx* ctx, const float* d_descA, int64_t n1, const float* d_d
       float* sbox = (float*)(base + o_sbox);
       match_superbox10_kernel<<<(unsigned)((n_super + 127) / 128), 128, 0, ctx->stream>>>(box, n_tiles, sbox);
       VO_CHECK_LAUNCH(ctx, "match_superbox10_kernel");
+      // this call's share of the sorted rows (all of them unless the rows are sharded along the curve)
+      const long long seg_lo = rows * curve_shard / n_curve_shards, seg_hi = rows * (curve_shard + 1) / n_curve_shards;
+      const long long seg_rows = seg_hi - seg_lo;
+      if (n_curve_shards > 1) VO_CUDA(ctx, cudaMemsetAsync(pi, 0xFF, (size_t)rows * 4, ctx->stream));  // others: no match
       // warps per 32-row group: enough to give every SM ~32 warps when the rows alone cannot
-      const long long groups = (rows + 31) / 32;
+      const long long groups = (seg_rows + 31) / 32;
       int n_warps = 1;
       // measured (exp/match_mid.py, rows x 1M columns): 64 resident warps per SM pay from ~2048 row groups on
       // (65536 rows 2.38 -> 2.28 ms, 131072 rows 3.75 -> 3.45 ms), 32 are better below (16384 rows 1.27 vs 1.34 ms)
@@ -1306,16 +1351,20 @@ int vo_match_dev(vo_ctx* ctx, const float* d_descA, int64_t n1, const float* d_d
       if (mma_smem > 48 * 1024)
         VO_CUDA(ctx, cudaFuncSetAttribute(match_scan10_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           1024 + kMaxScanWarps * kMmaWarpSmem));
+      if (groups > 0)
       match_scan10_mma_kernel<<<(unsigned)groups, 32 * n_warps, mma_smem, ctx->stream>>>(
-          d_descA, row_begin, rows, sorted_ids, keys2, rec, orig, frag, box, sbox, ckeys2, n2, mm, range_flag, pb, ps, pi);
+          d_descA, row_begin, seg_rows, sorted_ids + seg_lo, keys2 + seg_lo, rec, orig, frag, box, sbox, ckeys2, n2, mm,
+          range_flag, pb, ps, pi);
       VO_CHECK_LAUNCH(ctx, "match_scan10_mma_kernel");
       const size_t scan_smem = (size_t)n_warps * kTileBytes;
       static_assert(kTileBytes >= 3 * 32 * 4, "merge arrays reuse the tile buffers");
       if (scan_smem > 48 * 1024)
         VO_CUDA(ctx, cudaFuncSetAttribute(match_scan10_indexed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           kMaxScanWarps * kTileBytes));
+      if (groups > 0)
       match_scan10_indexed_kernel<<<(unsigned)groups, 32 * n_warps, scan_smem, ctx->stream>>>(
-          d_descA, row_begin, rows, sorted_ids, keys2, rec, orig, box, sbox, ckeys2, n2, range_flag, pb, ps, pi);
+          d_descA, row_begin, seg_rows, sorted_ids + seg_lo, keys2 + seg_lo, rec, orig, box, sbox, ckeys2, n2, range_flag,
+          pb, ps, pi);
       VO_CHECK_LAUNCH(ctx, "match_scan10_indexed_kernel");
     }
   }
@@ -1336,6 +1385,10 @@ int vo_match_dev(vo_ctx* ctx, const float* d_descA, int64_t n1, const float* d_d
       flags, idx, counts, rows, row_begin, capacity, want_ids ? d_idA : nullptr, want_ids ? d_idB : nullptr,
       reinterpret_cast<int2*>(d_pairs_out), d_correct);
   VO_CHECK_LAUNCH(ctx, "match_scatter_kernel");
+  if (d_match_idx) {
+    match_idx_kernel<<<(unsigned)merge_blocks, 256, 0, ctx->stream>>>(flags, idx, rows, d_match_idx);
+    VO_CHECK_LAUNCH(ctx, "match_idx_kernel");
+  }
   if (want_ids && n2 > 0) {
     VO_CUDA(ctx, cudaMemsetAsync(table, 0xFF, (size_t)table_size * 8, ctx->stream));
     idjoin_build_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, ctx->stream>>>(d_idB, n2, table, table_size - 1);
@@ -1356,6 +1409,77 @@ int vo_match_dev(vo_ctx* ctx, const float* d_descA, int64_t n1, const float* d_d
     stats[0] = (int64_t)((unsigned long long*)h)[2];
   }
   if (total > capacity) return vo_set_error(ctx, VO_ERR_CAPACITY, "vo_match", "pairs_out capacity");
+  return VO_OK;
+}
+
+extern "C" {
+
+int vo_match_dev(vo_ctx* ctx, const float* d_descA, int64_t n1, const float* d_descB, int64_t n2, int dim,
+                 float dist_thr, float ratio_thr, const int32_t* d_idA, const int32_t* d_idB, int64_t row_begin,
+                 int64_t row_end, int32_t* d_pairs_out, int64_t capacity, int64_t* n_out, int64_t stats[2],
+                 float* d_best, float* d_second, int32_t* d_best_idx) {
+  return match_dev_impl(ctx, d_descA, n1, d_descB, n2, dim, dist_thr, ratio_thr, d_idA, d_idB, row_begin, row_end,
+                        d_pairs_out, capacity, n_out, stats, d_best, d_second, d_best_idx, 0, 1, nullptr);
+}
+
+int vo_match_compact_dev(vo_ctx* ctx, const int32_t* d_match_idx, int64_t n1, int32_t* d_pairs_out, int64_t capacity,
+                         int64_t* n_out) {
+  if (!ctx || !n_out) return VO_ERR_INVALID;
+  int st = vo_ctx_activate(ctx);
+  if (st) return st;
+  *n_out = 0;
+  VO_REQUIRE(ctx, n1 >= 0 && n1 < 0x7fffffffLL && capacity >= 0, "vo_match_compact: sizes");
+  if (n1 == 0) return VO_OK;
+  VO_REQUIRE(ctx, d_match_idx && (capacity == 0 || d_pairs_out), "vo_match_compact: null buffers");
+  const long long blocks = (n1 + 255) / 256;
+  size_t off = 0;
+  auto carve = [&](size_t bytes) { size_t o = off; off = vo_align_up(off + bytes, 256); return o; };
+  const size_t o_flags = carve((size_t)n1), o_counts = carve((size_t)blocks * 4), o_small = carve(64);
+  char* base;
+  st = vo_scratch(ctx, off, (void**)&base);
+  if (st) return st;
+  unsigned char* flags = (unsigned char*)(base + o_flags);
+  int* counts = (int*)(base + o_counts);
+  long long* d_total = (long long*)(base + o_small);
+  match_idx_flags_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(d_match_idx, n1, flags, counts);
+  VO_CHECK_LAUNCH(ctx, "match_idx_flags_kernel");
+  st = vo_scan_block_counts(ctx, counts, blocks, d_total);
+  if (st) return st;
+  match_scatter_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(flags, d_match_idx, counts, n1, 0, capacity, nullptr,
+                                                                 nullptr, reinterpret_cast<int2*>(d_pairs_out), nullptr);
+  VO_CHECK_LAUNCH(ctx, "match_scatter_kernel");
+  void* h;
+  st = vo_pinned(ctx, 64, &h);
+  if (st) return st;
+  VO_CUDA(ctx, cudaMemcpyAsync(h, d_total, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  VO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  *n_out = *(long long*)h;
+  if (*n_out > capacity) return vo_set_error(ctx, VO_ERR_CAPACITY, "vo_match_compact", "pairs_out capacity");
+  return VO_OK;
+}
+
+int vo_match_sharded_dev(vo_ctx* ctx, const float* d_descA, int64_t n1, const float* d_descB, int64_t n2, int dim,
+                         float dist_thr, float ratio_thr, int shard, int n_shards, int32_t* d_match_idx,
+                         int32_t* d_pairs_out, int64_t capacity, int64_t* n_out) {
+  if (!ctx || !n_out) return VO_ERR_INVALID;
+  VO_REQUIRE(ctx, d_match_idx != nullptr, "vo_match_sharded: d_match_idx");
+  VO_REQUIRE(ctx, n_shards >= 1 && shard >= 0 && shard < n_shards, "vo_match_sharded: shard");
+  VO_REQUIRE(ctx, n_shards == 1 || ctx->nccl_comm == nullptr || ctx->n_ranks == n_shards,
+             "vo_match_sharded: n_shards must equal the communicator size");
+  *n_out = 0;
+  if (n1 == 0) return VO_OK;
+  int64_t n_mine = 0;
+  // (1) this shard's rows; everybody else's come out as -1
+  int st = match_dev_impl(ctx, d_descA, n1, d_descB, n2, dim, dist_thr, ratio_thr, nullptr, nullptr, 0, n1, nullptr, 0,
+                          &n_mine, nullptr, nullptr, nullptr, nullptr, shard, n_shards, d_match_idx);
+  if (st != VO_OK && st != VO_ERR_CAPACITY) return st;  // (capacity 0: only the per-row result is wanted here)
+  // (2) the exchange: every row is owned by exactly one shard, so an element-wise MAX merges the shards' results
+  if (n_shards > 1 && ctx->nccl_comm) {
+    st = vo_comm_allreduce_max_i32(ctx, d_match_idx, n1);
+    if (st) return st;
+  }
+  // (3) the accepted pairs in ascending row order (identical on every rank after the exchange)
+  if (capacity > 0 || d_pairs_out) return vo_match_compact_dev(ctx, d_match_idx, n1, d_pairs_out, capacity, n_out);
   return VO_OK;
 }
 

@@ -121,7 +121,12 @@ __global__ void __launch_bounds__(kSeqThreads, VO_SEQ_MINB) seq_pipeline_kernel(
   float* const poses = a.poses + seq * (long long)a.n_frames * 12;
   // (constant memory, not a per-thread array: a dynamically indexed local copy was found clobbered by the
   // cheirality stage's stack temporaries in one build - see profiles/r01_sequences.md)
+#ifdef VO_SEQ_LOCAL_IDENTITY  // the round-1 form, kept for exp/seq_clobber_probe.py (profiles/r02_sequences.md)
+  const float I12_local[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+  const float* const I12 = I12_local;
+#else
   const float* const I12 = kIdentity12;
+#endif
 
   if (tid < 12)
     for (int f = 0; f < a.n_frames; ++f) poses[f * 12 + tid] = I12[tid];

@@ -76,6 +76,7 @@ int vo_ctx_activate(vo_ctx* ctx);
 
 // all-reduce (sum) of n doubles in place on the context stream; no-op without a communicator
 int vo_comm_allreduce_f64(vo_ctx* ctx, double* d_buf, int n);
+int vo_comm_allreduce_max_i32(vo_ctx* ctx, int32_t* d_buf, long long n);
 
 // in-place exclusive scan of per-block counts by one CTA (fixed order); *d_total = grand total
 int vo_scan_block_counts(vo_ctx* ctx, int* d_counts, long long n_blocks, long long* d_total);

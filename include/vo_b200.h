@@ -189,6 +189,21 @@ int vo_match_dev(vo_ctx* ctx, const float* d_descA, int64_t n1, const float* d_d
                  int32_t* d_pairs_out, int64_t capacity, int64_t* n_out, int64_t stats[2],
                  float* d_best, float* d_second, int32_t* d_best_idx);
 
+/* Sharded matching with its exchange step (BASELINE config 4 across the GPUs of a box): shard `shard` of `n_shards`
+ * scans its share of ALL n1 rows against the replicated B and writes d_match_idx[n1] (device): the matched column
+ * of a row it owns, -1 for rejected rows and for rows of other shards.  On the indexed path (dim 10, large sets) the
+ * shards are contiguous segments of the rows' MORTON ORDER, not of their index range: every shard then sees the row
+ * density of the unsharded problem and the index prunes as well as on one GPU (row blocks by index prune 2x worse
+ * at 8 shards).  With a communicator attached (vo_ctx_comm_init, n_ranks == n_shards) the per-row results are then
+ * merged by one element-wise MAX all-reduce of n1 int32 over NVLink, and the accepted pairs (i, best_j) are
+ * compacted in ascending i: every rank ends with the identical, complete result of match_points.
+ * vo_match_compact_dev is step 3 alone (for callers that exchange d_match_idx themselves). */
+int vo_match_sharded_dev(vo_ctx* ctx, const float* d_descA, int64_t n1, const float* d_descB, int64_t n2, int dim,
+                         float dist_thr, float ratio_thr, int shard, int n_shards, int32_t* d_match_idx,
+                         int32_t* d_pairs_out, int64_t capacity, int64_t* n_out);
+int vo_match_compact_dev(vo_ctx* ctx, const int32_t* d_match_idx, int64_t n1, int32_t* d_pairs_out, int64_t capacity,
+                         int64_t* n_out);
+
 /* Which of the matcher's paths runs (diagnostics, parity tests and bench.py; every path returns the identical
  * bit-exact result): AUTO picks by size; BRUTE = the plain tiled distance-matrix scan over ALL n1*n2 pairs
  * (any dim); ORDERED = Morton-ordered rows + packed exact scan with the early-exit bound (dim 10);

@@ -299,3 +299,32 @@ def test_match_pruning_hostile_sets(ctx, oracle, seed):
     assert np.array_equal(best.view(np.uint32), rb.view(np.uint32))
     assert np.array_equal(second.view(np.uint32), rs.view(np.uint32))
     assert np.array_equal(pairs, rp)
+
+
+@pytest.mark.parametrize("n1,n2,dim,n_shards", [(9000, 20000, 10, 4), (40000, 9000, 10, 8), (300, 1000, 7, 3), (5, 40, 10, 8)])
+def test_match_sharded_equals_unsharded(ctx, oracle, n1, n2, dim, n_shards):
+    """vo_match_sharded_dev shard by shard on one GPU (no communicator: the exchange is done here with an element-wise
+    maximum, which is what the MAX all-reduce computes): every row is owned by exactly one shard - a Morton-order
+    segment on the indexed path, an index block otherwise - and the merged result is the oracle's match list."""
+    import torch
+    A, B = synth.descriptors(n1, n2, dim=dim, seed=5 + n1, dup_frac=0.02, noise=0.02)
+    rp, _ = oracle.match(A, B, 0.2, 0.8, n_threads=8)
+    dA, dB = torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda()
+    merged = torch.full((n1,), -1, dtype=torch.int32, device="cuda")
+    owned_total = 0
+    for shard in range(n_shards):
+        m = torch.full((n1,), -7, dtype=torch.int32, device="cuda")
+        ctx.match_sharded_dev(dA.data_ptr(), n1, dB.data_ptr(), n2, dim, shard, n_shards, m.data_ptr())
+        torch.cuda.synchronize()
+        assert int(m.min()) >= -1  # every element written
+        assert not bool(((m >= 0) & (merged >= 0)).any())  # no row answered by two shards
+        owned_total += int((m >= 0).sum())
+        merged = torch.maximum(merged, m)
+    pairs = torch.empty((n1, 2), dtype=torch.int32, device="cuda")
+    n = ctx.match_compact_dev(merged.data_ptr(), n1, pairs.data_ptr(), n1)
+    assert n == len(rp) == owned_total
+    assert np.array_equal(pairs[:n].cpu().numpy(), rp)
+    # one shard = the plain call
+    m1 = torch.empty((n1,), dtype=torch.int32, device="cuda")
+    n_one = ctx.match_sharded_dev(dA.data_ptr(), n1, dB.data_ptr(), n2, dim, 0, 1, m1.data_ptr(), pairs.data_ptr(), n1)
+    assert n_one == len(rp) and torch.equal(m1, merged)

@@ -63,6 +63,14 @@ def _worker(rank, world, port, out_dir):
         res[mode + "_pose"] = s.get_pose()
         s.close()
         dist.barrier()
+    # sharded matching with its exchange (MAX all-reduce of the per-row results over NCCL): identical on every rank
+    A, B = synth.descriptors(30000, 20000, seed=3, noise=0.02)
+    dA, dB = torch.from_numpy(A).to(dev), torch.from_numpy(B).to(dev)
+    midx = torch.empty(30000, dtype=torch.int32, device=dev)
+    mp_ = torch.empty((30000, 2), dtype=torch.int32, device=dev)
+    nm = ctx.match_sharded_dev(dA.data_ptr(), 30000, dB.data_ptr(), 20000, 10, rank, world, midx.data_ptr(), mp_.data_ptr(), 30000)
+    res["match_pairs"] = mp_[:nm].cpu().numpy()
+    res["match_idx"] = midx.cpu().numpy()
     np.savez(os.path.join(out_dir, f"rank{rank}.npz"), **res)
     ctx.peer_detach()
     ctx.comm_destroy()
@@ -98,6 +106,11 @@ def test_sharded_picp_nccl_and_fused_peer_exchange(tmp_path):
         assert np.abs(r0[mode + "_n"] - single_n).max() <= 4
         assert np.abs(r0[mode + "_H"] - lin["H"]).max() <= 1e-5 * np.abs(lin["H"]).max()
         assert np.abs(r0[mode + "_pose"] - s.get_pose()).max() <= 1e-6
+    # sharded matching: both ranks hold the complete, identical match list = the unsharded call
+    A, B = synth.descriptors(30000, 20000, seed=3, noise=0.02)
+    ref_pairs, _ = ctx.match(A, B)
+    assert np.array_equal(r0["match_pairs"], r1["match_pairs"]) and np.array_equal(r0["match_idx"], r1["match_idx"])
+    assert np.array_equal(r0["match_pairs"], ref_pairs)
     # the two exchange mechanisms sum the same two numbers: identical bits
     assert np.array_equal(r0["nccl_pose"], r0["peer_pose"])
     s.close()
