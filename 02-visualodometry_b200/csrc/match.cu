@@ -646,6 +646,41 @@ __device__ __forceinline__ float exact_sqdist10(const float* __restrict__ rc, co
   const float d = __fadd_rn(__fadd_rn(__fadd_rn(q0, q1), __fadd_rn(q2, q3)), __fadd_rn(__fadd_rn(q4, q5), __fadd_rn(q6, q7)));
   return __fadd_rn(__fadd_rn(d, q8), q9);
 }
+// The dense-tile fallback of match_scan10_mma_kernel (see the guard there): every column of a 128-column tile for
+// all 32 rows of the warp, two columns per packed instruction, in the exact twin's arithmetic.  Out of line on
+// purpose: inlined into the tile loop it cost the common, filtered path 12 % (1M x 1M: 16.3 vs 14.5 ms) through
+// register allocation alone.
+struct Best3 {
+  float best, second, bound;
+  int idx;
+};
+__device__ __noinline__ Best3 dense_tile_scan(const float* __restrict__ rec, const int* __restrict__ orig, long long j0,
+                                              int cnt, float a0, float a1, float a2, float a3, float a4, float a5,
+                                              float a6, float a7, float a8, float a9, Best3 c) {
+  const int n_pairs = (cnt + 1) >> 1;
+  const float4* src = reinterpret_cast<const float4*>(rec + (j0 >> 1) * kPairFloats);
+  const f2 b0 = pack2(a0, a0), b1 = pack2(a1, a1), b2 = pack2(a2, a2), b3 = pack2(a3, a3), b4 = pack2(a4, a4);
+  const f2 b5 = pack2(a5, a5), b6 = pack2(a6, a6), b7 = pack2(a7, a7), b8 = pack2(a8, a8), b9 = pack2(a9, a9);
+  for (int p = 0; p < n_pairs; ++p) {
+    const float4 v0 = __ldg(src + 5 * p), v1 = __ldg(src + 5 * p + 1), v2 = __ldg(src + 5 * p + 2);
+    const float4 v3 = __ldg(src + 5 * p + 3), v4 = __ldg(src + 5 * p + 4);
+    const f2 x0 = sq2(pack2(v0.x, v0.y), b0), x4 = sq2(pack2(v0.z, v0.w), b1);
+    const f2 x2 = sq2(pack2(v1.x, v1.y), b2), x6 = sq2(pack2(v1.z, v1.w), b3);
+    const f2 x1 = sq2(pack2(v2.x, v2.y), b4), x5 = sq2(pack2(v2.z, v2.w), b5);
+    const f2 x3 = sq2(pack2(v3.x, v3.y), b6), x7 = sq2(pack2(v3.z, v3.w), b7);
+    const f2 x8 = sq2(pack2(v4.x, v4.y), b8), x9 = sq2(pack2(v4.z, v4.w), b9);
+    f2 d = add2(add2(add2(x0, x4), add2(x2, x6)), add2(add2(x1, x5), add2(x3, x7)));
+    d = add2(add2(d, x8), x9);
+    float d0, d1;
+    unpack2(d, d0, d1);
+    if (!__any_sync(0xffffffffu, (d0 <= c.bound) || (d1 <= c.bound))) continue;
+    if (d0 <= c.bound) update_best_tie(d0, __ldg(orig + j0 + 2 * p), c.best, c.second, c.idx);
+    if (2 * p + 1 < cnt && d1 <= c.bound) update_best_tie(d1, __ldg(orig + j0 + 2 * p + 1), c.best, c.second, c.idx);
+    c.bound = fminf(c.bound, c.second);
+  }
+  return c;
+}
+
 // Same walk, same bounds and same merge as match_scan10_indexed_kernel; the per-tile work is the filter.
 #ifndef VO_MMA_LB
 #define VO_MMA_LB 32 * kMaxScanWarps
@@ -721,6 +756,7 @@ __global__ void __launch_bounds__(VO_MMA_LB) match_scan10_mma_kernel(
   float best = FLT_MAX, second = FLT_MAX, bound = FLT_MAX;
   int idx = -1;
   int dense_skip = 0;  // tiles still to be evaluated outright before the filter is probed again (warp-uniform)
+  int dense_streak = 0;  // consecutive filtered tiles that turned out dense
   // The rows' bounds ride in the A operand (k = 14,15, held by the threads with tq == 3): the MMA output is v - bound,
   // a column survives iff its output is <= 0, and a running 3-input minimum over 4 column blocks needs one
   // comparison.  (The bound joins the sum as two more terms; if it dwarfs the others the sign is decided anyway.)
@@ -868,36 +904,26 @@ __global__ void __launch_bounds__(VO_MMA_LB) match_scan10_mma_kernel(
         if (!dense) {
           if (!__any_sync(0xffffffffu, mine)) continue;
           const int kept = __popc(mk.x) + __popc(mk.y) + __popc(mk.z) + __popc(mk.w);
-          if (VO_MATCH_DENSE_GUARD && __reduce_max_sync(0xffffffffu, kept) >= kDenseMinPerRow) {
+          if (VO_MATCH_DENSE_GUARD && __any_sync(0xffffffffu, kept >= kDenseMinPerRow)) {
             dense = true;
-            dense_skip = kDenseSkip;
+            // the first tiles of every walk are dense by construction (no second-best yet: everything survives);
+            // only a REPEAT means the data defeats the filter, and only then are the next tiles taken unfiltered
+            if (++dense_streak >= 2) dense_skip = kDenseSkip;
             if (mine) *reinterpret_cast<uint4*>(mask + lane * 4) = make_uint4(0, 0, 0, 0);
+          } else {
+            dense_streak = 0;
           }
         }
         if (dense) {
           VO_COUNT(3, 1);
           const long long j0 = t * kTileRows;
           const int cnt = (int)((n2 - j0 < kTileRows) ? (n2 - j0) : kTileRows);
-          const int n_pairs = (cnt + 1) >> 1;
-          const float4* src = reinterpret_cast<const float4*>(rec + (j0 >> 1) * kPairFloats);
-          auto bc = [](float x) { return pack2(x, x); };
-          for (int p = 0; p < n_pairs; ++p) {
-            const float4 v0 = __ldg(src + 5 * p), v1 = __ldg(src + 5 * p + 1), v2 = __ldg(src + 5 * p + 2);
-            const float4 v3 = __ldg(src + 5 * p + 3), v4 = __ldg(src + 5 * p + 4);
-            const f2 x0 = sq2(pack2(v0.x, v0.y), bc(a[0])), x4 = sq2(pack2(v0.z, v0.w), bc(a[1]));
-            const f2 x2 = sq2(pack2(v1.x, v1.y), bc(a[2])), x6 = sq2(pack2(v1.z, v1.w), bc(a[3]));
-            const f2 x1 = sq2(pack2(v2.x, v2.y), bc(a[4])), x5 = sq2(pack2(v2.z, v2.w), bc(a[5]));
-            const f2 x3 = sq2(pack2(v3.x, v3.y), bc(a[6])), x7 = sq2(pack2(v3.z, v3.w), bc(a[7]));
-            const f2 x8 = sq2(pack2(v4.x, v4.y), bc(a[8])), x9 = sq2(pack2(v4.z, v4.w), bc(a[9]));
-            f2 d = add2(add2(add2(x0, x4), add2(x2, x6)), add2(add2(x1, x5), add2(x3, x7)));
-            d = add2(add2(d, x8), x9);
-            float d0, d1;
-            unpack2(d, d0, d1);
-            if (!__any_sync(0xffffffffu, (d0 <= bound) || (d1 <= bound))) continue;
-            if (d0 <= bound) update_best_tie(d0, __ldg(orig + j0 + 2 * p), best, second, idx);
-            if (2 * p + 1 < cnt && d1 <= bound) update_best_tie(d1, __ldg(orig + j0 + 2 * p + 1), best, second, idx);
-            bound = fminf(bound, second);
-          }
+          Best3 cur = {best, second, bound, idx};
+          cur = dense_tile_scan(rec, orig, j0, cnt, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], cur);
+          best = cur.best;
+          second = cur.second;
+          bound = cur.bound;
+          idx = cur.idx;
         } else if (mine) {
           *reinterpret_cast<uint4*>(mask + lane * 4) = make_uint4(0, 0, 0, 0);
           auto survivors = [&](unsigned bits, int w) {
