@@ -120,7 +120,7 @@ _sig("vo_seq_batch_run_dev", C.c_int, _vp, C.POINTER(SeqParams), C.c_int, C.c_in
 from .sharding import N_TERMS, pack_terms, shard_bounds, shard_range, unpack_terms  # noqa: E402,F401
 
 MAX_ROUNDS = 64
-MODE_AUTO, MODE_STREAM, MODE_RESIDENT = 0, 1, 2
+MODE_AUTO, MODE_STREAM, MODE_RESIDENT, MODE_STREAM_PERSISTENT = 0, 1, 2, 3
 STATUS_SKIPPED, STATUS_INLIER, STATUS_OUTLIER = 0, 1, 2
 
 

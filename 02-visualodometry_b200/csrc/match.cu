@@ -631,7 +631,8 @@ __device__ __forceinline__ float min3(float a, float b, float c) {  // FMNMX3; N
 #define VO_MATCH_DENSE_GUARD 1
 #endif
 constexpr int kDenseMinPerRow = 48;  // survivors of one row in a 128-column tile from which the outright scan is cheaper
-constexpr int kDenseSkip = 7;        // tiles evaluated outright after a dense one before the filter is tried again
+constexpr int kDenseSkip = 3;        // tiles evaluated outright, once the data has shown itself filter-proof, before the filter is tried again
+constexpr int kDenseStreak = 3;      // consecutive dense tiles that count as filter-proof data (the first tiles of every walk are dense anyway)
 constexpr int kFragBufs = VO_MMA_BUFS;             // tile fragment buffers per warp (TMA bulk copies in flight)
 constexpr int kFragTileBytes = kTileRows * 32;     // 128 columns x 16 bf16
 constexpr int kMmaWarpSmem = 2048 + kFragBufs * kFragTileBytes + 64;
@@ -685,7 +686,7 @@ __device__ __noinline__ Best3 dense_tile_scan(const float* __restrict__ rec, con
 #ifndef VO_MMA_LB
 #define VO_MMA_LB 32 * kMaxScanWarps
 #endif
-__global__ void __launch_bounds__(VO_MMA_LB) match_scan10_mma_kernel(
+__global__ void __launch_bounds__(VO_MMA_LB, 2) match_scan10_mma_kernel(
     const float* __restrict__ A, long long row_begin, long long rows, const unsigned* __restrict__ row_order,
     const unsigned* __restrict__ row_keys_sorted, const float* __restrict__ rec, const int* __restrict__ orig,
     const uint2* __restrict__ frag, const float* __restrict__ box, const float* __restrict__ sbox,
@@ -908,7 +909,7 @@ __global__ void __launch_bounds__(VO_MMA_LB) match_scan10_mma_kernel(
             dense = true;
             // the first tiles of every walk are dense by construction (no second-best yet: everything survives);
             // only a REPEAT means the data defeats the filter, and only then are the next tiles taken unfiltered
-            if (++dense_streak >= 2) dense_skip = kDenseSkip;
+            if (++dense_streak >= kDenseStreak) dense_skip = kDenseSkip;
             if (mine) *reinterpret_cast<uint4*>(mask + lane * 4) = make_uint4(0, 0, 0, 0);
           } else {
             dense_streak = 0;

@@ -620,6 +620,153 @@ __device__ __forceinline__ void st_poll(unsigned long long* p, unsigned long lon
   asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+// named-barrier helpers: the persistent kernels synchronise their COMPUTE threads only (the streaming variant has a
+// producer warp that must not take part)
+__device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ bool named_bar_or(int id, int n, bool pred) {
+  int r;
+  asm volatile(
+      "{\n.reg .pred p, q;\nsetp.ne.s32 p, %3, 0;\nbar.red.or.pred q, %1, %2, p;\nselp.s32 %0, 1, 0, q;\n}\n"
+      : "=r"(r)
+      : "r"(id), "r"(n), "r"((int)pred)
+      : "memory");
+  return r != 0;
+}
+
+struct RoundCtx {
+  PicpDev* dev;
+  unsigned long long* ll;
+  unsigned ll_seq0;
+  int ll_stride;
+  float damping, rel_tol;
+  int peer_n, peer_rank;
+  VoMailbox* const* peers;
+};
+
+// The end of one Gauss-Newton round of a persistent kernel, executed by the N_THREADS compute threads of every CTA
+// (named barrier BAR): s_part[warp][term] holds the warps' sums.  Publishes the CTA's partial as self-validating
+// words, collects all CTAs' partials (every CTA on one GPU; CTA 0 only with peers, which then pushes the GPU's sums
+// into every rank's mailbox while every CTA polls its own GPU's mailbox), solves the damped 6x6 system redundantly in
+// every CTA, applies the increment to s_pose and sets *s_stop (0 go on, 1 converged, 2 a wait timed out).
+template <int BAR, int N_THREADS>
+__device__ __forceinline__ void round_exchange_and_solve(const RoundCtx& a, int r, unsigned mb_seq0, VoMailbox* me,
+                                                         float (*s_part)[kSlots], double (*s_fin)[kSlots], double* s_tot,
+                                                         float* s_pose, float* s_dx, int* s_stop, float& prev_chi) {
+  constexpr int WARPS = N_THREADS / 32;
+  constexpr int BATCH = (kResMaxGrid + WARPS - 1) / WARPS;  // L2 loads in flight per polling thread
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool multi_cta = gridDim.x > 1;
+  const bool peers = a.peer_n > 1;
+  const bool collect = multi_cta && (!peers || blockIdx.x == 0);  // this CTA adds up the GPU's partials
+  named_bar_sync(BAR, N_THREADS);
+  const unsigned seq = a.ll_seq0 + 1u + (unsigned)r;
+  bool timed_out = false;
+  if (multi_cta) {
+    unsigned long long* buf = a.ll + (size_t)(seq & 1u) * a.ll_stride * kSlots;
+    if (warp == 0) {  // publish this CTA's partial: term `lane`, warps added in warp order
+      float p = 0.f;
+#pragma unroll
+      for (int w = 0; w < WARPS; ++w) p += s_part[w][lane];
+      st_poll(buf + (size_t)blockIdx.x * kSlots + lane, (unsigned long long)__float_as_uint(p) | ((unsigned long long)seq << 32));
+    }
+    if (collect) {  // thread (warp, lane): term `lane` of CTAs warp, warp + WARPS, ...: all loads in flight at once
+      unsigned long long w[BATCH];
+      long long spins = 0;
+      for (;;) {
+        bool ok = true;
+#pragma unroll
+        for (int u = 0; u < BATCH; ++u) {
+          const unsigned b = warp + u * WARPS;
+          w[u] = (b < gridDim.x) ? ld_poll(buf + (size_t)b * kSlots + lane) : ((unsigned long long)seq << 32);
+        }
+#pragma unroll
+        for (int u = 0; u < BATCH; ++u) ok = ok && ((unsigned)(w[u] >> 32) == seq);
+        if (ok) break;
+        if (++spins > kResSpinLimit) {
+          timed_out = true;
+          break;
+        }
+      }
+      double v = 0.0;
+#pragma unroll
+      for (int u = 0; u < BATCH; ++u) {
+        const unsigned b = warp + u * WARPS;
+        if (b < gridDim.x) v += (double)__uint_as_float((unsigned)w[u]);
+      }
+      s_fin[warp][lane] = v;
+    }
+  }
+  if (named_bar_or(BAR, N_THREADS, timed_out)) {
+    if (tid == 0) {
+      a.dev->timeout = 1;
+      *s_stop = 2;
+    }
+    named_bar_sync(BAR, N_THREADS);
+    return;
+  }
+  if (warp == 0) {
+    double tot = 0.0;
+    if (collect) {
+#pragma unroll
+      for (int w = 0; w < WARPS; ++w) tot += s_fin[w][lane];
+    } else if (!multi_cta) {
+#pragma unroll
+      for (int w = 0; w < WARPS; ++w) tot += (double)s_part[w][lane];
+    }
+    bool ok = true;
+    if (peers) {
+      const unsigned mseq = mb_seq0 + 1u + (unsigned)r;
+      const int par = (int)(mseq & 1u);
+      if (blockIdx.x == 0) {  // the GPU's sums -> every rank's mailbox (mine included), 8-byte self-validating words
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(tot), tag = (unsigned long long)mseq << 32;
+        const unsigned long long w0 = (bits & 0xffffffffull) | tag, w1 = (bits >> 32) | tag;
+        for (int p = 0; p < a.peer_n; ++p) {
+          volatile unsigned long long* dst = &a.peers[p]->ll[par][a.peer_rank][lane][0];
+          dst[0] = w0;
+          dst[1] = w1;
+        }
+      }
+      // every CTA: term `lane` of every rank out of this GPU's mailbox, added in RANK order
+      ok = peer_collect(me, par, mseq, a.peer_n, lane, tot);
+      ok = __all_sync(0xffffffffu, ok);
+    }
+    s_tot[lane] = tot;
+    __syncwarp();
+    if (lane == 0) {
+      float Hu[21], bb[6];
+#pragma unroll
+      for (int k = 0; k < 21; ++k) Hu[k] = (float)s_tot[k];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) bb[k] = (float)s_tot[21 + k];
+      float dx[6];
+      picp_gn_solve(Hu, bb, a.damping, dx);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) s_dx[k] = dx[k];
+      vo_picp_stats st;
+      st.chi_inliers = (float)s_tot[27];
+      st.chi_outliers = (float)s_tot[28];
+      st.num_inliers = (int)s_tot[29];
+      st.num_outliers = (int)s_tot[30];
+      if (blockIdx.x == 0 && r < VO_PICP_MAX_ROUNDS) a.dev->stats[r] = st;
+      int stop = 0;
+      if (a.rel_tol >= 0.f) {  // exec/icp_test.cpp:99-106
+        const float cur = st.chi_inliers;
+        const float rel = (prev_chi > 1e-10f) ? __fdiv_rn(fabsf(__fsub_rn(prev_chi, cur)), prev_chi) : 0.f;
+        if (rel < a.rel_tol) stop = 1;
+        prev_chi = cur;
+      }
+      if (!ok) {
+        stop = 2;
+        me->timeout = 1u;
+      }
+      *s_stop = stop;
+    }
+    __syncwarp();
+    picp_apply_dx_warp(s_dx, s_pose, lane);
+  }
+  named_bar_sync(BAR, N_THREADS);
+}
+
 template <bool KEEP, bool PINHOLE>
 __global__ void __launch_bounds__(kResThreads, 1) picp_resident_kernel(const ResArgs a) {
   extern __shared__ __align__(16) float4 s_pl[];  // [5 planes][quads_per_cta]: wx wy wz zu zv of 4 correspondences
@@ -635,9 +782,7 @@ __global__ void __launch_bounds__(kResThreads, 1) picp_resident_kernel(const Res
   const long long qb = (long long)blockIdx.x * qpc;
   const long long qe = (qb + qpc < n_quads) ? qb + qpc : n_quads;
   const int nq = qe > qb ? (int)(qe - qb) : 0;
-  const bool multi_cta = gridDim.x > 1;
   const bool peers = a.peer_n > 1;
-  const bool collect = multi_cta && (!peers || blockIdx.x == 0);  // this CTA adds up the GPU's partials
 
   // ---- gather once: (first: image index, second: world index) -> the CTA's planes in shared memory
   {
@@ -716,111 +861,10 @@ __global__ void __launch_bounds__(kResThreads, 1) picp_resident_kernel(const Res
       v[31] = 0.f;
       s_part[warp][lane] = warp_sum32_scatter(v, lane);
     }
-    __syncthreads();
-    const unsigned seq = a.ll_seq0 + 1u + (unsigned)r;
-    bool timed_out = false;
-    if (multi_cta) {
-      unsigned long long* buf = a.ll + (size_t)(seq & 1u) * a.ll_stride * kSlots;
-      if (warp == 0) {  // publish this CTA's partial: term `lane`, warps added in warp order
-        float p = 0.f;
-#pragma unroll
-        for (int w = 0; w < kResWarps; ++w) p += s_part[w][lane];
-        st_poll(buf + (size_t)blockIdx.x * kSlots + lane, (unsigned long long)__float_as_uint(p) | ((unsigned long long)seq << 32));
-      }
-      if (collect) {  // thread (warp, lane): term `lane` of CTAs warp, warp + kResWarps, ... all loads in flight at once
-        unsigned long long w[kResBatch];
-        long long spins = 0;
-        for (;;) {
-          bool ok = true;
-#pragma unroll
-          for (int u = 0; u < kResBatch; ++u) {
-            const unsigned b = warp + u * kResWarps;
-            w[u] = (b < gridDim.x) ? ld_poll(buf + (size_t)b * kSlots + lane) : ((unsigned long long)seq << 32);
-          }
-#pragma unroll
-          for (int u = 0; u < kResBatch; ++u) ok = ok && ((unsigned)(w[u] >> 32) == seq);
-          if (ok) break;
-          if (++spins > kResSpinLimit) {
-            timed_out = true;
-            break;
-          }
-        }
-        double v = 0.0;
-#pragma unroll
-        for (int u = 0; u < kResBatch; ++u) {
-          const unsigned b = warp + u * kResWarps;
-          if (b < gridDim.x) v += (double)__uint_as_float((unsigned)w[u]);
-        }
-        s_fin[warp][lane] = v;
-      }
-    }
-    if (__syncthreads_or(timed_out)) {
-      if (tid == 0) a.dev->timeout = 1;
-      if (tid == 0) s_stop = 2;
-      __syncthreads();
-      break;
-    }
-    if (warp == 0) {
-      double tot = 0.0;
-      if (collect) {
-#pragma unroll
-        for (int w = 0; w < kResWarps; ++w) tot += s_fin[w][lane];
-      } else if (!multi_cta) {
-#pragma unroll
-        for (int w = 0; w < kResWarps; ++w) tot += (double)s_part[w][lane];
-      }
-      bool ok = true;
-      if (peers) {
-        const unsigned mseq = mb_seq0 + 1u + (unsigned)r;
-        const int par = (int)(mseq & 1u);
-        if (blockIdx.x == 0) {  // the GPU's sums -> every rank's mailbox (mine included), 8-byte self-validating words
-          const unsigned long long bits = (unsigned long long)__double_as_longlong(tot), tag = (unsigned long long)mseq << 32;
-          const unsigned long long w0 = (bits & 0xffffffffull) | tag, w1 = (bits >> 32) | tag;
-          for (int p = 0; p < a.peer_n; ++p) {
-            volatile unsigned long long* dst = &a.peers[p]->ll[par][a.peer_rank][lane][0];
-            dst[0] = w0;
-            dst[1] = w1;
-          }
-        }
-        // every CTA: term `lane` of every rank out of this GPU's mailbox, added in RANK order
-        ok = peer_collect(me, par, mseq, a.peer_n, lane, tot);
-        ok = __all_sync(0xffffffffu, ok);
-      }
-      s_tot[lane] = tot;
-      __syncwarp();
-      if (lane == 0) {
-        float Hu[21], bb[6];
-#pragma unroll
-        for (int k = 0; k < 21; ++k) Hu[k] = (float)s_tot[k];
-#pragma unroll
-        for (int k = 0; k < 6; ++k) bb[k] = (float)s_tot[21 + k];
-        float dx[6];
-        picp_gn_solve(Hu, bb, a.damping, dx);
-#pragma unroll
-        for (int k = 0; k < 6; ++k) s_dx[k] = dx[k];
-        vo_picp_stats st;
-        st.chi_inliers = (float)s_tot[27];
-        st.chi_outliers = (float)s_tot[28];
-        st.num_inliers = (int)s_tot[29];
-        st.num_outliers = (int)s_tot[30];
-        if (blockIdx.x == 0 && r < VO_PICP_MAX_ROUNDS) a.dev->stats[r] = st;
-        int stop = 0;
-        if (a.rel_tol >= 0.f) {  // exec/icp_test.cpp:99-106
-          const float cur = st.chi_inliers;
-          const float rel = (prev_chi > 1e-10f) ? __fdiv_rn(fabsf(__fsub_rn(prev_chi, cur)), prev_chi) : 0.f;
-          if (rel < a.rel_tol) stop = 1;
-          prev_chi = cur;
-        }
-        if (!ok) {
-          stop = 2;
-          me->timeout = 1u;
-        }
-        s_stop = stop;
-      }
-      __syncwarp();
-      picp_apply_dx_warp(s_dx, s_pose, lane);
-    }
-    __syncthreads();
+    RoundCtx rc;
+    rc.dev = a.dev; rc.ll = a.ll; rc.ll_seq0 = a.ll_seq0; rc.ll_stride = a.ll_stride; rc.damping = a.damping;
+    rc.rel_tol = a.rel_tol; rc.peer_n = a.peer_n; rc.peer_rank = a.peer_rank; rc.peers = a.peers;
+    round_exchange_and_solve<0, kResThreads>(rc, r, mb_seq0, me, s_part, s_fin, s_tot, s_pose, s_dx, &s_stop, prev_chi);
     if (s_stop) {
       ++r;
       break;
@@ -834,6 +878,189 @@ __global__ void __launch_bounds__(kResThreads, 1) picp_resident_kernel(const Res
       a.dev->prev_chi = prev_chi;
       a.dev->rel_tol = a.rel_tol;
       if (peers) *(volatile unsigned*)&me->seq = mb_seq0 + (unsigned)r;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ persistent streaming kernel (all rounds, one launch)
+// For a correspondence set too large for shared memory (the 10 M frame on 1, 2 or 4 GPUs): the tile ring, the
+// producer lane and the consumer arithmetic of picp_linearize_kernel, wrapped in the round loop of the resident
+// kernel.  The packed planes do not depend on the pose, so the producer simply keeps streaming - round after round,
+// the first tiles of round r+1 already in the ring while the consumers reduce, exchange and solve round r - and the
+// serial tail of the one-launch-per-round design (ticket, last-CTA pass 2, solve, launch hand-over: ~7.6 us) is
+// replaced by the one all-to-all exchange of round_exchange_and_solve (~2 us).  With the device-side convergence
+// test (rel_tol >= 0) the producer waits for a round's verdict before it fetches the next round's tiles.
+struct StreamArgs {
+  const float* pk;
+  long long n;
+  long long stride;
+  PicpCam cam;
+  float thr, damping, rel_tol;
+  int n_rounds;
+  PicpDev* dev;
+  unsigned long long* ll;
+  unsigned ll_seq0;
+  int ll_stride;
+  int peer_n, peer_rank;
+  VoMailbox* peers[VO_MAX_PEERS];
+};
+
+__device__ __forceinline__ bool mbar_try_wait_hint(unsigned long long* bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.u32 %0, 1, 0, p;\n}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
+      : "memory");
+  return ok != 0;
+}
+
+template <bool KEEP, bool PINHOLE>
+__global__ void __launch_bounds__(kLinThreads, 1) picp_stream_rounds_kernel(const StreamArgs a) {
+  extern __shared__ __align__(128) float s_tiles[];
+  __shared__ __align__(8) unsigned long long s_full[kStages], s_empty[kStages];
+  __shared__ float s_pose[12];
+  __shared__ float s_part[kWarps][kSlots];
+  __shared__ double s_fin[kWarps][kSlots];
+  __shared__ double s_tot[kSlots];
+  __shared__ float s_dx[6];
+  __shared__ int s_stop;        // 0 go on, 1 converged, 2 a wait timed out
+  __shared__ int s_round_done;  // rounds whose verdict is in s_stop (read by the producer)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+#pragma unroll
+    for (int st = 0; st < kStages; ++st) {
+      mbar_init(&s_full[st], 1);
+      mbar_init(&s_empty[st], kWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    s_stop = 0;
+    s_round_done = 0;
+  }
+  if (tid < 12) s_pose[tid] = a.dev->pose[tid];
+  __syncthreads();
+  const long long n_tiles = (a.n + kTile - 1) / kTile;
+
+  if (warp == kWarps) {
+    // ---------------- producer: one elected lane streams every round's tiles through the ring
+    if (lane != 0) return;
+    long long it = 0;
+    bool aborted = false;
+    auto issue = [&](long long t, long long i) {
+      const int stage = (int)(i % kStages);
+      const long long first = t * kTile;
+      const long long left = ((a.n + 3) & ~3ll) - first;
+      const unsigned bytes = (unsigned)((left < kTile ? left : kTile) * sizeof(float));
+      float* dst = s_tiles + (size_t)stage * 5 * kTile;
+      mbar_arrive_expect_tx(&s_full[stage], 5u * bytes);
+#pragma unroll
+      for (int p = 0; p < 5; ++p) bulk_g2s(dst + p * kTile, a.pk + p * a.stride + first, bytes, &s_full[stage]);
+    };
+    for (int r = 0; r < a.n_rounds && !aborted; ++r) {
+      if (a.rel_tol >= 0.f && r > 0) {  // the verdict of round r-1 first: never fetch a round that will not run
+        while (*(volatile int*)&s_round_done < r && *(volatile int*)&s_stop != 2) {}
+        if (*(volatile int*)&s_stop) break;
+      }
+      for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+        if (it >= kStages) {
+          const int stage = (int)(it % kStages);
+          const unsigned phase = (unsigned)(it / kStages) & 1u;
+          while (!mbar_try_wait_hint(&s_empty[stage], phase ^ 1u)) {
+            if (*(volatile int*)&s_stop == 2) {  // the consumers gave up (a wait for another CTA / GPU expired)
+              aborted = true;
+              break;
+            }
+          }
+          if (aborted) break;
+        }
+        issue(t, it);
+      }
+    }
+    if (aborted) {  // copies in flight must land before the CTA may exit
+      const long long first = it > kStages ? it - kStages : 0;
+      for (long long j = first; j < it; ++j) mbar_wait(&s_full[j % kStages], (unsigned)(j / kStages) & 1u);
+    }
+    return;
+  }
+
+  // ---------------- consumers
+  VoMailbox* me = a.peer_n > 1 ? a.peers[a.peer_rank] : nullptr;
+  const unsigned mb_seq0 = me ? *(volatile unsigned*)&me->seq : 0u;
+  float prev_chi = FLT_MAX;  // (lane 0 of warp 0)
+  RoundCtx rc;
+  rc.dev = a.dev; rc.ll = a.ll; rc.ll_seq0 = a.ll_seq0; rc.ll_stride = a.ll_stride; rc.damping = a.damping;
+  rc.rel_tol = a.rel_tol; rc.peer_n = a.peer_n; rc.peer_rank = a.peer_rank; rc.peers = a.peers;
+  long long it = 0;
+  int r = 0;
+  for (; r < a.n_rounds; ++r) {
+    float T[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) T[i] = s_pose[i];
+    f2 acc2[29];
+#pragma unroll
+    for (int i = 0; i < 29; ++i) acc2[i] = 0ull;
+    int n_in = 0, n_out = 0;
+    for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+      const int stage = (int)(it % kStages);
+      const unsigned phase = (unsigned)(it / kStages) & 1u;
+      mbar_wait(&s_full[stage], phase);
+      const float4* tile = reinterpret_cast<const float4*>(s_tiles + (size_t)stage * 5 * kTile);
+      const long long base = t * kTile + 4ll * tid;
+      float4 wx, wy, wz, zu, zv;
+      const bool any = base < a.n;
+      if (any) {
+        wx = tile[tid];
+        wy = tile[kThreads + tid];
+        wz = tile[2 * kThreads + tid];
+        zu = tile[3 * kThreads + tid];
+        zv = tile[4 * kThreads + tid];
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[stage]);  // values are in registers: hand the stage back
+      if (!any) continue;
+      int s0, s1, s2, s3;
+      const long long left = a.n - base;
+      PairState pa, pb;
+      pair_front<PINHOLE>(a.cam, T, wx.x, wy.x, wz.x, wx.y, wy.y, wz.y, pa);
+      pair_front<PINHOLE>(a.cam, T, wx.z, wy.z, wz.z, wx.w, wy.w, wz.w, pb);
+      if (pa.fix0 || pa.fix1 || pb.fix0 || pb.fix1) {
+        pair_fix(a.cam, pa);
+        pair_fix(a.cam, pb);
+      }
+      pair_back<KEEP, PINHOLE>(a.cam, a.thr, pa, zu.x, zv.x, zu.y, zv.y, true, left > 1, acc2, n_in, n_out, s0, s1);
+      pair_back<KEEP, PINHOLE>(a.cam, a.thr, pb, zu.z, zv.z, zu.w, zv.w, left > 2, left > 3, acc2, n_in, n_out, s2, s3);
+    }
+    {  // warp reduction: lane L ends up with the warp's total of term L (per-warp counts are exact in float)
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 29; ++i) {
+        float lo, hi;
+        unpack2(acc2[i], lo, hi);
+        v[i] = lo + hi;
+      }
+      v[29] = (float)n_in;
+      v[30] = (float)n_out;
+      v[31] = 0.f;
+      s_part[warp][lane] = warp_sum32_scatter(v, lane);
+    }
+    round_exchange_and_solve<1, kThreads>(rc, r, mb_seq0, me, s_part, s_fin, s_tot, s_pose, s_dx, &s_stop, prev_chi);
+    if (tid == 0) {
+      __threadfence_block();
+      *(volatile int*)&s_round_done = r + 1;
+    }
+    if (s_stop) {
+      ++r;
+      break;
+    }
+  }
+  if (blockIdx.x == 0) {
+    if (tid < 12) a.dev->pose[tid] = s_pose[tid];
+    if (tid == 0) {
+      a.dev->round = r;
+      a.dev->stop = (s_stop == 1);
+      a.dev->prev_chi = prev_chi;
+      a.dev->rel_tol = a.rel_tol;
+      if (me) *(volatile unsigned*)&me->seq = mb_seq0 + (unsigned)r;
     }
   }
 }
@@ -945,6 +1172,11 @@ cudaError_t lin_opt_in_all() {
   if (e == cudaSuccess) e = cudaFuncSetAttribute(picp_resident_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, res_smem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(picp_resident_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, res_smem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(picp_resident_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, res_smem);
+  const int lin_smem = (int)kLinSmemBytes;
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(picp_stream_rounds_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lin_smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(picp_stream_rounds_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lin_smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(picp_stream_rounds_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lin_smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(picp_stream_rounds_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lin_smem);
   return e;
 }
 
@@ -1081,7 +1313,7 @@ struct ResPlan { int grid, quads_per_cta; size_t smem; };
 ResPlan resident_plan(const vo_picp* s, int n_rounds) {
   ResPlan p = {0, 0, 0};
   const vo_ctx* ctx = s->ctx;
-  if (s->mode == VO_PICP_MODE_STREAM) return p;
+  if (s->mode == VO_PICP_MODE_STREAM || s->mode == VO_PICP_MODE_STREAM_PERSISTENT) return p;
   if (ctx->nccl_comm != nullptr && ctx->peer_n <= 1) return p;  // NCCL-only exchange happens between launches
   if (s->mode == VO_PICP_MODE_AUTO && n_rounds < 2 && s->packed) return p;  // one round of a packed set: stream 20 B
   const long long n_quads = (s->n_pairs + 3) / 4;
@@ -1146,6 +1378,65 @@ int launch_resident(vo_picp* s, const ResPlan& pl, float thr, float damping, boo
   else e = s->pinhole ? launch_res2<false, true>(pl, ctx->stream, a) : launch_res2<false, false>(pl, ctx->stream, a);
   ctx->launches++;
   if (e != cudaSuccess) return vo_set_error(ctx, VO_ERR_CUDA, "picp_resident_kernel", cudaGetErrorString(e));
+  return VO_OK;
+}
+
+template <bool KEEP, bool PINHOLE>
+cudaError_t launch_sr2(int grid, cudaStream_t st, const StreamArgs& a) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kLinThreads);
+  cfg.dynamicSmemBytes = kLinSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;  // all CTAs co-resident: they wait for each other's partials
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = grid > 1 ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, picp_stream_rounds_kernel<KEEP, PINHOLE>, a);
+}
+
+// can this solve run as ONE persistent streaming launch?  (needs the in-kernel exchange: no NCCL-only communicator)
+bool stream_rounds_ok(const vo_picp* s, int n_rounds) {
+  const vo_ctx* ctx = s->ctx;
+  if (ctx->nccl_comm != nullptr && ctx->peer_n <= 1) return false;
+  if (s->mode == VO_PICP_MODE_STREAM_PERSISTENT) return true;
+  return s->mode == VO_PICP_MODE_AUTO && n_rounds >= 2;
+}
+
+// n_rounds Gauss-Newton rounds over the packed planes in ONE persistent launch (picp_stream_rounds_kernel)
+int launch_stream_rounds(vo_picp* s, float thr, float damping, bool keep, int n_rounds, float rel_tol) {
+  vo_ctx* ctx = s->ctx;
+  int st = ensure_packed(s);
+  if (st) return st;
+  if (s->ll_seq > 0xF0000000u) {
+    VO_CUDA(ctx, cudaMemsetAsync(s->d_ll, 0, sizeof(unsigned long long) * 2 * kResMaxGrid * kSlots, ctx->stream));
+    s->ll_seq = 0;
+  }
+  StreamArgs a;
+  a.pk = s->d_pk;
+  a.n = s->n_pairs;
+  a.stride = s->n_pad;
+  a.cam = s->cam;
+  a.thr = thr;
+  a.damping = damping;
+  a.rel_tol = rel_tol;
+  a.n_rounds = n_rounds;
+  a.dev = s->d_dev;
+  a.ll = s->d_ll;
+  a.ll_seq0 = s->ll_seq;
+  a.ll_stride = kResMaxGrid;
+  a.peer_n = ctx->peer_n > 1 ? ctx->peer_n : 0;
+  a.peer_rank = ctx->peer_rank;
+  for (int p = 0; p < VO_MAX_PEERS; ++p) a.peers[p] = (VoMailbox*)ctx->peer_mailbox[p];
+  s->ll_seq += (unsigned)n_rounds;
+  int grid = grid_for(s);
+  if (grid > kResMaxGrid) grid = kResMaxGrid;
+  cudaError_t e;
+  if (keep) e = s->pinhole ? launch_sr2<true, true>(grid, ctx->stream, a) : launch_sr2<true, false>(grid, ctx->stream, a);
+  else e = s->pinhole ? launch_sr2<false, true>(grid, ctx->stream, a) : launch_sr2<false, false>(grid, ctx->stream, a);
+  ctx->launches++;
+  if (e != cudaSuccess) return vo_set_error(ctx, VO_ERR_CUDA, "picp_stream_rounds_kernel", cudaGetErrorString(e));
   return VO_OK;
 }
 
@@ -1388,7 +1679,7 @@ int vo_picp_pack(vo_picp* s) {
 }
 
 int vo_picp_set_mode(vo_picp* s, int mode) {
-  if (!s || mode < VO_PICP_MODE_AUTO || mode > VO_PICP_MODE_RESIDENT) return VO_ERR_INVALID;
+  if (!s || mode < VO_PICP_MODE_AUTO || mode > VO_PICP_MODE_STREAM_PERSISTENT) return VO_ERR_INVALID;
   s->mode = mode;
   return VO_OK;
 }
@@ -1467,6 +1758,7 @@ int vo_picp_enqueue_rounds(vo_picp* s, float thr, float damping, int keep_outlie
   if (pl.grid > 0) return n_rounds ? launch_resident(s, pl, thr, damping, keep_outliers != 0, n_rounds, -1.f) : VO_OK;
   if (s->mode == VO_PICP_MODE_RESIDENT)
     return vo_set_error(s->ctx, VO_ERR_CAPACITY, "vo_picp_enqueue_rounds", "VO_PICP_MODE_RESIDENT: the set does not fit shared memory");
+  if (stream_rounds_ok(s, n_rounds)) return n_rounds ? launch_stream_rounds(s, thr, damping, keep_outliers != 0, n_rounds, -1.f) : VO_OK;
   st = reset_rounds(s, -1.f);
   if (st) return st;
   for (int r = 0; r < n_rounds; ++r) {
@@ -1530,6 +1822,14 @@ int vo_picp_solve(vo_picp* s, float thr, float damping, int keep_outliers, int m
   const ResPlan pl = resident_plan(s, max_rounds);
   if (pl.grid > 0) {  // the whole driver loop in one launch: the convergence test runs inside the kernel
     st = launch_resident(s, pl, thr, damping, keep_outliers != 0, max_rounds, rel_tol);
+    if (st) return st;
+    st = check_dev_flags(s, "vo_picp_solve");
+    if (st) return st;
+    VO_CUDA(ctx, cudaMemcpyAsync(h, &s->d_dev->round, sizeof(Head), cudaMemcpyDeviceToHost, ctx->stream));
+    VO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    done = ((Head*)h)->round;
+  } else if (s->mode != VO_PICP_MODE_RESIDENT && stream_rounds_ok(s, max_rounds)) {
+    st = launch_stream_rounds(s, thr, damping, keep_outliers != 0, max_rounds, rel_tol);
     if (st) return st;
     st = check_dev_flags(s, "vo_picp_solve");
     if (st) return st;

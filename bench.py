@@ -252,7 +252,8 @@ def bench_picp(args, vo, torch, dist, ctx, dev, stream, local, rank, world, scal
     round_ms = max_over_ranks(k_ms[len(k_ms) // 2]) / ROUNDS
     peak, peak_src = measured_peaks()
     achieved = ALGO_BYTES_PER_CORR * C / (round_ms * 1e-3) / 1e9
-    kernel = "picp_resident_kernel" if resident else "picp_linearize_kernel"
+    persistent = (not resident) and (not multi or ctx.peer_active)  # AUTO: ONE persistent streaming launch per solve
+    kernel = "picp_resident_kernel" if resident else ("picp_stream_rounds_kernel" if persistent else "picp_linearize_kernel")
     roofline = {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": ALGO_BYTES_PER_CORR * C, "us_per_launch": round_ms * 1e3,
@@ -265,6 +266,9 @@ def bench_picp(args, vo, torch, dist, ctx, dev, stream, local, rank, world, scal
     else:
         roofline["streamed_bytes_per_launch"] = 20 * C
         roofline["dram_frac_streamed"] = 20 * C / (round_ms * 1e-3) / 1e9 / peak
+        if persistent:
+            roofline["launch_definition"] = ("ONE persistent launch streams the packed planes through the TMA ring once per "
+                                             "round; 'launch' = one Gauss-Newton round = launch duration / rounds")
         roofline["note"] = ("achieved counts the 28 B/correspondence the reference's linearize reads (SURVEY 8(d)); the "
                             "kernel streams the 20 B/correspondence planes gathered once per frame by picp_pack_kernel "
                             "(dram_frac_streamed = real DRAM utilisation); it is FP32-issue bound, not HBM bound "
@@ -614,8 +618,16 @@ def simulate_sequences_torch(torch, dev, n_seq, n_frames, seed, max_pts=128, chu
 
 def bench_sequences(args, ctx, vo, torch, dev, stream, rank, world, barrier, max_over_ranks):
     """BASELINE config 5: 4096 independent 121-frame sequences (full exec/icp_test.cpp loop per sequence),
-    sequences sharded over the ranks, no communication."""
-    total, F, P, W = 4096, 121, 128, 1024
+    sequences sharded over the ranks, no communication; at N > 1 also the weak-scaling line (4096 per GPU)."""
+    out = _bench_sequences(4096, "sequences", args, ctx, vo, torch, dev, stream, rank, world, barrier, max_over_ranks)
+    if world > 1:
+        out.update(_bench_sequences(4096 * world, "sequences_weak_scaling", args, ctx, vo, torch, dev, stream, rank, world,
+                                    barrier, max_over_ranks))
+    return out
+
+
+def _bench_sequences(total, key, args, ctx, vo, torch, dev, stream, rank, world, barrier, max_over_ranks):
+    F, P, W = 121, 128, 1024
     lo, hi = vo.shard_range(total, world, rank)
     S = hi - lo
     cnt, uv, desc, ids = simulate_sequences_torch(torch, dev, S, F, seed=42 + rank)
@@ -643,7 +655,7 @@ def bench_sequences(args, ctx, vo, torch, dev, stream, rank, world, barrier, max
     barrier()
     ms = max_over_ranks(a.elapsed_time(b)) / steps
     ok = int((status == 0).sum().item())
-    return {"sequences": {"metric": "sequences_per_s", "value": total / (ms * 1e-3), "frames_per_s": total * F / (ms * 1e-3),
+    return {key: {"metric": "sequences_per_s", "value": total / (ms * 1e-3), "frames_per_s": total * F / (ms * 1e-3),
                           "unit": "sequences/s", "ms_per_batch": ms, "n_sequences": total, "n_frames": F,
                           "sequences_per_gpu": S, "ok_rank0": ok, "mean_rounds_per_frame": float(rounds[:, 1:].float().mean().item()),
                           "mean_world_points": float(wcnt.float().mean().item()),

@@ -129,18 +129,22 @@ int vo_picp_set_correspondences(vo_picp* s, const int32_t* pairs, int64_t n_pair
  * of range is reported by the next vo_picp_fetch_stats / vo_picp_solve / vo_picp_linearize (VO_ERR_INVALID). */
 int vo_picp_set_correspondences_dev(vo_picp* s, const int32_t* d_pairs, int64_t n_pairs);
 /* Which kernel runs the Gauss-Newton rounds (diagnostic; results agree to float rounding, masks bit for bit):
- * AUTO: a set that fits the machine's shared memory (vo_picp_resident_capacity, 1.67 M correspondences on a B200)
- *       and is solved for >= 2 rounds per call runs in ONE persistent cooperative launch with the correspondences
- *       resident in shared memory across all rounds; anything else streams the packed planes once per round.
- * STREAM / RESIDENT force one of the two (RESIDENT fails with VO_ERR_CAPACITY when the set does not fit). */
-/* Builds the streaming kernel's packed planes of the current set now (picp_pack_kernel, 48 B per correspondence of
- * traffic) instead of lazily inside the first streamed round; a no-op when they exist. */
-int vo_picp_pack(vo_picp* s);
+ * AUTO: a solve of >= 2 rounds per call runs as ONE persistent cooperative launch - with the correspondences
+ *       RESIDENT in shared memory across all rounds when the set fits the machine's shared memory
+ *       (vo_picp_resident_capacity, 1.67 M correspondences on a B200), else STREAM_PERSISTENT: the packed planes
+ *       streamed through the TMA ring every round; the rounds exchange their sums inside the kernel.  A single round
+ *       (vo_picp_one_round) and a context with an NCCL-only communicator use STREAM: one launch per round.
+ * STREAM / RESIDENT / STREAM_PERSISTENT force one of the three (RESIDENT fails with VO_ERR_CAPACITY when the set
+ * does not fit). */
 #define VO_PICP_MODE_AUTO 0
 #define VO_PICP_MODE_STREAM 1
 #define VO_PICP_MODE_RESIDENT 2
+#define VO_PICP_MODE_STREAM_PERSISTENT 3
 int vo_picp_set_mode(vo_picp* s, int mode);
 int vo_picp_resident_capacity(const vo_picp* s, int64_t* n_pairs_max);
+/* Builds the streaming kernels' packed planes of the current set now (picp_pack_kernel, 48 B per correspondence of
+ * traffic) instead of lazily inside the first streamed round; a no-op when they exist. */
+int vo_picp_pack(vo_picp* s);
 /* PICPSolver::linearize (picp_solver.cpp:56-91) at the current pose, no state change.
  * H is the full symmetric 6x6; status (nullable) gets one VO_PICP_* byte per correspondence. */
 int vo_picp_linearize(vo_picp* s, float kernel_threshold, int keep_outliers,

@@ -167,7 +167,7 @@ def test_empty_and_invalid_correspondences(ctx):
     s2.close()
 
 
-@pytest.mark.parametrize("mode", [1, 2], ids=["stream", "resident"])
+@pytest.mark.parametrize("mode", [1, 2, 3], ids=["stream", "resident", "stream_persistent"])
 @pytest.mark.parametrize("n,permute,thr,keep,rounds", [(50000, False, 3000.0, False, 10), (50000, True, 100.0, True, 10),
                                                        (120, False, 3000.0, False, 8), (300000, False, 1000.0, False, 5)])
 def test_rounds_track_oracle(ctx, oracle, n, permute, thr, keep, rounds, mode):
@@ -197,7 +197,7 @@ def test_rounds_track_oracle(ctx, oracle, n, permute, thr, keep, rounds, mode):
     s2.close()
 
 
-@pytest.mark.parametrize("mode", [1, 2], ids=["stream", "resident"])
+@pytest.mark.parametrize("mode", [1, 2, 3], ids=["stream", "resident", "stream_persistent"])
 def test_device_side_convergence_loop(ctx, oracle, mode):
     """vo_picp_solve == the driver loop of exec/icp_test.cpp:88-107 run with synchronous rounds."""
     fr = synth.picp_frame(n=20000, seed=11)
@@ -273,6 +273,35 @@ def test_resident_matches_streaming(ctx, oracle):
         assert np.abs(p1 - p2).max() <= 1e-6, n
 
 
+@pytest.mark.parametrize("n", [1, 1407, 1409, 148 * 1408 + 5, 3_000_001])
+def test_persistent_streaming_matches_per_round_launches(ctx, n):
+    """the persistent streaming kernel (all rounds in one cooperative launch, planes streamed through the TMA ring
+    every round) against one launch per round on the same packed planes: the exact part is the same code, the sums
+    are reduced in a different (fixed) order - counts identical in round 0, within the knife-edge slack later, chi
+    1e-5, pose 1e-6; two runs are bit-identical; the in-kernel convergence test stops at the same round."""
+    fr = synth.picp_frame(n=n, seed=3 + n, permute=(n % 2 == 1))
+    res = {}
+    for mode in (1, 3, 3):
+        s = _solver(ctx, fr, mode=mode)
+        s.enqueue_rounds(3000.0, 1.0, False, 7)
+        res.setdefault(mode, []).append((s.fetch_stats(7), s.get_pose()))
+        s.close()
+    (st1, p1), (st3, p3), (st3b, p3b) = res[1][0], res[3][0], res[3][1]
+    assert np.array_equal(p3, p3b) and [x.chi_inliers for x in st3] == [x.chi_inliers for x in st3b]
+    assert st1[0].num_inliers == st3[0].num_inliers and st1[0].num_outliers == st3[0].num_outliers
+    for r in range(7):
+        assert abs(st1[r].num_inliers - st3[r].num_inliers) <= (0 if r == 0 else max(2, int(1e-5 * n))), r
+        assert abs(st1[r].chi_inliers - st3[r].chi_inliers) <= 1e-5 * max(st1[r].chi_inliers, 1.0), r
+    assert np.abs(p1 - p3).max() <= 1e-6
+    if n >= 1000:
+        done = {}
+        for mode in (1, 3):
+            s = _solver(ctx, fr, mode=mode)
+            done[mode] = s.solve(3000.0, 1.0, False, max_rounds=40, rel_tol=1e-3)[0]
+            s.close()
+        assert done[1] == done[3]
+
+
 def test_resident_capacity_and_fallback(ctx):
     """a set one correspondence above the resident capacity: AUTO streams it, RESIDENT refuses it"""
     vo = product()
@@ -322,7 +351,7 @@ def test_resident_is_deterministic_and_restartable(ctx):
     assert [x.num_inliers for x in st] == outs[0][1][3:]
 
 
-@pytest.mark.parametrize("mode", [1, 2], ids=["stream", "resident"])
+@pytest.mark.parametrize("mode", [1, 2, 3], ids=["stream", "resident", "stream_persistent"])
 def test_out_of_range_index_on_the_device_path(ctx, mode):
     """set_correspondences_dev cannot validate synchronously: the bad index is reported by the next fetch / solve,
     and a following valid set works (the flag does not stick)."""
