@@ -88,6 +88,20 @@ __device__ __forceinline__ bool accept_match(int idx, float best, float second, 
 
 __constant__ float kIdentity12[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
 
+// -DVO_SEQ_STAGE_CLOCKS (exp/build_variant.sh seqclk): thread 0 of every CTA accumulates clock64() per stage of the
+// frame loop: 0 frame loads, 1 match against the map, 2 PICP rounds, 3 pose + match against the previous frame +
+// anti-join, 4 triangulate + append, 5 initialisation (frames 0/1).  Read with vo_debug_seq_stage_cycles.
+#ifdef VO_SEQ_STAGE_CLOCKS
+__device__ unsigned long long g_seq_stage[8];
+#define VO_SEQ_CLK_DECL long long clk_t = clock64(); unsigned long long clk_acc[6] = {0, 0, 0, 0, 0, 0}
+#define VO_SEQ_CLK(i) do { const long long n_ = clock64(); clk_acc[i] += (unsigned long long)(n_ - clk_t); clk_t = n_; } while (0)
+#define VO_SEQ_CLK_FLUSH do { if (threadIdx.x == 0) for (int i_ = 0; i_ < 6; ++i_) atomicAdd(&g_seq_stage[i_], clk_acc[i_]); } while (0)
+#else
+#define VO_SEQ_CLK_DECL do { } while (0)
+#define VO_SEQ_CLK(i) do { } while (0)
+#define VO_SEQ_CLK_FLUSH do { } while (0)
+#endif
+
 #ifndef VO_SEQ_MINB
 #define VO_SEQ_MINB 6
 #endif
@@ -112,6 +126,7 @@ __global__ void __launch_bounds__(kSeqThreads, VO_SEQ_MINB) seq_pipeline_kernel(
 
   const long long seq = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  VO_SEQ_CLK_DECL;
   const PicpCam cam = {{a.p.K[0], a.p.K[1], a.p.K[2], a.p.K[3], a.p.K[4], a.p.K[5], a.p.K[6], a.p.K[7], a.p.K[8]},
                        (float)(a.p.cols - 1), (float)(a.p.rows - 1)};
   const bool pinhole = a.p.K[1] == 0.f && a.p.K[3] == 0.f && a.p.K[6] == 0.f && a.p.K[7] == 0.f && a.p.K[8] == 1.f;
@@ -227,10 +242,12 @@ __global__ void __launch_bounds__(kSeqThreads, VO_SEQ_MINB) seq_pipeline_kernel(
     __syncthreads();
   }
 
+  VO_SEQ_CLK(5);
   // ------------------------------------------------------------ frame loop (icp_test.cpp:61-136)
   for (int f = 0; f + 1 < a.n_frames; ++f) {
     load_frame(a, seq, f, s_curr);
     load_frame(a, seq, f + 1, s_next);
+    VO_SEQ_CLK(0);
     const int W = s_wcnt;
     // (1) next frame against the map
     float best = FLT_MAX, second = FLT_MAX;
@@ -256,6 +273,7 @@ __global__ void __launch_bounds__(kSeqThreads, VO_SEQ_MINB) seq_pipeline_kernel(
     s_matched[tid] = acc_w ? 1 : 0;  // id_meas == index inside the frame
     if (tid < 12) s_prev[tid] = poses[f * 12 + tid];
     __syncthreads();
+    VO_SEQ_CLK(1);
     // (2) PICP from the previous pose (icp_test.cpp:78-107)
     if (tid == 0) {
       pose_inverse_dev(s_prev, s_pose);
@@ -353,6 +371,7 @@ __global__ void __launch_bounds__(kSeqThreads, VO_SEQ_MINB) seq_pipeline_kernel(
       const bool stop = verdict.x != 0;
       if (stop) break;
     }
+    VO_SEQ_CLK(2);
     // (3) estimated camera-in-world pose of the next frame
     if (tid == 0) {
       pose_inverse_dev(s_pose, s_est);
@@ -387,6 +406,7 @@ __global__ void __launch_bounds__(kSeqThreads, VO_SEQ_MINB) seq_pipeline_kernel(
     const bool fresh = acc_m && !s_matched[idx];
     int n_new;
     const int pos_n = block_compact(fresh, s_warp, n_new);
+    VO_SEQ_CLK(3);
     // (6) triangulate the new pairs between the two poses and append them to the map (cam.cpp:94-140)
     if (tid == 0) {
       projection_matrix_dev(a.p.K, s_prev, s_P1);
@@ -409,11 +429,24 @@ __global__ void __launch_bounds__(kSeqThreads, VO_SEQ_MINB) seq_pipeline_kernel(
     }
     __threadfence_block();
     __syncthreads();
+    VO_SEQ_CLK(4);
   }
   if (tid == 0) a.w_cnt[seq] = s_wcnt;
+  VO_SEQ_CLK_FLUSH;
 }
 
 }  // namespace
+
+#ifdef VO_SEQ_STAGE_CLOCKS
+extern "C" int vo_debug_seq_stage_cycles(unsigned long long out[8], int reset) {
+  if (cudaMemcpyFromSymbol(out, g_seq_stage, 64) != cudaSuccess) return VO_ERR_CUDA;
+  if (reset) {
+    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (cudaMemcpyToSymbol(g_seq_stage, z, 64) != cudaSuccess) return VO_ERR_CUDA;
+  }
+  return VO_OK;
+}
+#endif
 
 extern "C" {
 

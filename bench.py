@@ -123,7 +123,8 @@ def run_reference(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
             "higher_is_better": True, "scaling": args.scaling if args.gpus > 1 else "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": workload_config(1, args.scaling),
+            "config": workload_config(args.gpus, args.scaling if args.gpus > 1 else "weak",
+                                      "not applicable: the CPU reference solves the whole frame on the host cores"),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": f"full frame: {C_PER_GPU} correspondences x {ROUNDS} rounds per step, "
                                        f"{threads} threads (oracle/vo_oracle.cpp, -O2, correspondence-parallel)"},
