@@ -631,7 +631,7 @@ __device__ __forceinline__ float min3(float a, float b, float c) {  // FMNMX3; N
 #define VO_MATCH_DENSE_GUARD 1
 #endif
 constexpr int kDenseMinPerRow = 48;  // survivors of one row in a 128-column tile from which the outright scan is cheaper
-constexpr int kDenseSkip = 3;        // tiles evaluated outright, once the data has shown itself filter-proof, before the filter is tried again
+constexpr int kDenseSkip = 7;        // tiles evaluated outright, once the data has shown itself filter-proof, before the filter is tried again
 constexpr int kDenseStreak = 3;      // consecutive dense tiles that count as filter-proof data (the first tiles of every walk are dense anyway)
 constexpr int kFragBufs = VO_MMA_BUFS;             // tile fragment buffers per warp (TMA bulk copies in flight)
 constexpr int kFragTileBytes = kTileRows * 32;     // 128 columns x 16 bf16
