@@ -11,6 +11,8 @@
 #define CV_32F 5
 #define CV_64F 6
 
+typedef unsigned char uchar;  // OpenCV's global typedef (exec/pose_recovery_test.cpp:47)
+
 namespace cv {
 
 struct Point2f {

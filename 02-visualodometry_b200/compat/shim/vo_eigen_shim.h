@@ -55,6 +55,8 @@ class Matrix {
   int size() const { return R * C; }
   T* data() { return m; }
   const T* data() const { return m; }
+  Matrix& matrix() { return *this; }
+  const Matrix& matrix() const { return *this; }
   T& operator()(int r, int c) { return m[r * C + c]; }
   const T& operator()(int r, int c) const { return m[r * C + c]; }
   T& operator()(int i) { return m[i]; }

@@ -26,3 +26,11 @@ def read_outputs(out_dir):
                 traj_scaled=np.loadtxt(os.path.join(out_dir, "estimated_trajectory_scaled.txt")),
                 errors=np.loadtxt(os.path.join(out_dir, "errors.txt")),
                 world_points=np.loadtxt(os.path.join(out_dir, "estimated_world_points.txt")))
+
+
+def write_world_file(world_gt, path):
+    """data/world.dat of the reference: `id x y z d0..d9` per landmark (src/my_utilities.cpp:137-182)"""
+    with open(path, "w") as f:
+        for i in range(len(world_gt["id"])):
+            desc = " ".join("%.9g" % x for x in world_gt["desc"][i])
+            f.write("%d %.9g %.9g %.9g %s\n" % (world_gt["id"][i], *world_gt["xyz"][i], desc))

@@ -194,7 +194,7 @@ def _compat_bin(name):
 
 def test_unchanged_reference_mains_are_compiled_from_the_reference():
     """compat/exec/*.cpp are symlinks to the reference's own files: nothing of the drivers is copied or edited"""
-    for name in ("icp_test", "vo"):
+    for name in ("icp_test", "vo", "match_points_test", "triangulate_points_test", "pose_recovery_test"):
         _compat_bin(name)
         src = os.path.join(COMPAT_DIR, name + ".cpp")
         assert os.path.islink(src) and os.readlink(src) == f"/root/reference/exec/{name}.cpp"
@@ -251,3 +251,46 @@ def test_unchanged_reference_vo_runs(dataset, tmp_path):
         return [int(l.rsplit(" ", 1)[1]) for l in txt.splitlines() if l.startswith("Number of world points:")]
     assert counts(r.stdout) == counts(r2.stdout) and len(counts(r.stdout)) == 119
     assert "Absolute scale factor:" in r.stdout and "plotting skipped" in r.stdout
+
+
+@pytest.mark.gpu
+def test_unchanged_reference_test_mains(dataset, world_gt, tmp_path):
+    """The reference's three manual test mains (its whole 'test suite'), compiled unchanged against the
+    library and turned into known-answer tests on the bundled data:
+      exec/match_points_test.cpp        every accepted pair of every consecutive frame pair has equal id_real;
+      exec/pose_recovery_test.cpp       the recoverPose mask keeps every match wherever the robot translates;
+      exec/triangulate_points_test.cpp  the printed landmarks are data/world.dat's, up to the monocular scale."""
+    import re
+    dataset_io.write_meas_files(dataset, str(tmp_path / "data"))
+    dataset_io.write_world_file(world_gt, str(tmp_path / "data" / "world.dat"))
+
+    def run(name):
+        r = subprocess.run([_compat_bin(name)], cwd=str(tmp_path), capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, (name, r.stderr[-2000:])
+        return r.stdout
+
+    out = run("match_points_test")
+    rows = re.findall(r"Iteration: (\d+): matches: (\d+) / (\d+)", out)
+    assert len(rows) == 120 and all(a == b and int(b) > 0 for _, a, b in rows)
+    assert "Matches: Out of 115 possible matches, found 115, of which 115 are correct" in out
+
+    out = run("pose_recovery_test")
+    rows = [(int(a), int(b)) for a, b in re.findall(r"Inliers: (\d+) / (\d+)", out)]
+    assert len(rows) == 119 and all(a <= b for a, b in rows)
+    assert all(a == b for a, b in rows[:50])  # translating robot: every match passes the cheirality vote
+    assert "plotting skipped" in out
+
+    out = run("triangulate_points_test")
+    blocks = re.findall(r"Real ID world point: (\d+)\n([-\d.e+]+)\n([-\d.e+]+)\n([-\d.e+]+)", out)
+    assert len(blocks) == 115
+    ids = np.array([int(b[0]) for b in blocks])
+    X = np.array([[float(v) for v in b[1:]] for b in blocks])         # cameraToImage * X_cam0, baseline units
+    x, y, th = dataset["gt_pose"][0]
+    Rw = np.array([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1]])
+    Xr = (world_gt["xyz"][ids] - np.array([x, y, 0.0])) @ Rw             # landmarks in the robot frame of frame 0
+    Xr = Xr - world_gt["cam_in_robot"][:3, 3]                            # ... seen from the camera centre
+    scale = (X * Xr).sum() / (X * X).sum()
+    x1, y1, _ = dataset["gt_pose"][1]
+    assert abs(scale - np.hypot(x1 - x, y1 - y)) <= 1e-3 * scale         # = the true baseline between frames 0 and 1
+    err = np.linalg.norm(X * scale - Xr, axis=1) / np.linalg.norm(Xr, axis=1)
+    assert err.max() <= 5e-3, err.max()
