@@ -73,7 +73,9 @@ PICPSolver::PICPSolver()
       chi_outliers_(0.f), num_inliers_(0), corr_ptr_(nullptr), corr_size_(0), corr_hash_(0) {}
 
 void PICPSolver::init(const Camera& camera, const Vector3fVector& world_points, const Vector2fVector& image_points) {
-  if (!h_) h_ = std::make_shared<Handle>();
+  // The reference copies solvers by value (src/cam.cpp:33-34); copies of this class share the device state until one
+  // of them is initialised again, at which point it gets a device state of its own.
+  if (!h_ || h_.use_count() > 1) h_ = std::make_shared<Handle>();
   camera_ = camera;
   pose_stale_ = false;
   vo::check(vo_picp_set_camera(h_->p, camera.cameraMatrix().data(), camera.rows(), camera.cols(),
