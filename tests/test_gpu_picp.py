@@ -440,3 +440,18 @@ def test_full_size_properties(ctx):
         assert stats[-1].num_inliers > 0.85 * n
         assert np.abs(s.get_pose() - fr["pose_gt"]).max() < 1e-3
         s.close()
+
+
+@pytest.mark.parametrize("seed", [3, 4])
+def test_round_kernels_randomised_sweep(seed):
+    """exp/picp_rounds_stress.py: random sizes around the tile / grid / capacity boundaries, thresholds, keep_outliers,
+    pinhole and general K, identity and permuted pairs, 1..12 rounds and the in-kernel convergence test - the three round
+    kernels against each other (counts, chi 2e-5, pose 2e-6, same stopping round) and round 0 against the oracle"""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "exp", "picp_rounds_stress.py"), str(seed), "14"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert "mismatches: 0" in r.stdout
