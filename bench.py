@@ -536,6 +536,13 @@ def bench_matching(args, ctx, vo, torch, dev, rank, world, barrier, max_over_ran
                    "excludes ~90% of the 128-column tiles, a bf16 tensor-core lower bound most of the rest; survivors are "
                    "evaluated in the reference's fp32 order), so it is an equivalent rate, not arithmetic throughput: see "
                    "exact_brute_force for the roofline-bounded number"}
+    out["indexed_path_vs_tensor_pipe"] = {
+        "tiles_visited_per_32_row_group": "9.4 % of the 8192 128-column tiles (counters build, exp/match_count.py; a perfect "
+                                          "bound from the start would need 8.7 %, exp/prune_sim.py)",
+        "hmma_per_visited_tile": 32, "tensor_pipe_floor_ms_1Mx1M": 6.4,
+        "measured_over_floor_1gpu": (dt_blocks * 1e3 * world) / 6.4 if world == 1 else None,
+        "source": "profiles/r01_match_mma.md (25.3 M tile visits x 32 HMMA.16816 at ~8 cycles per SM sub-partition; ncu: tensor "
+                  "pipe 43.6 % active, issue slots 65 % busy)"}
     if rank == 0:
         # ---- the exact brute-force path (every pair evaluated in fp32, reference order): a 32768-row sample
         sub = min(32768, rows)
