@@ -1358,7 +1358,8 @@ int match_dev_impl(vo_ctx* ctx, const float* d_descA, int64_t n1, const float* d
       // measured (exp/match_mid.py, rows x 1M columns): 64 resident warps per SM pay from ~2048 row groups on
       // (65536 rows 2.38 -> 2.28 ms, 131072 rows 3.75 -> 3.45 ms), 32 are better below (16384 rows 1.27 vs 1.34 ms)
       static const long long env_budget = getenv("VO_MATCH_WARP_BUDGET") ? atoll(getenv("VO_MATCH_WARP_BUDGET")) : 0;
-      const long long warp_budget = env_budget > 0 ? env_budget : (groups >= 2048 ? 64 : 32);
+      // (round 2, 64-register kernel: 131072 rows 3.70 ms at a budget of 64, 3.55 ms at 128, 3.92 ms at 256)
+      const long long warp_budget = env_budget > 0 ? env_budget : (groups >= 4096 ? 128 : (groups >= 2048 ? 64 : 32));
       while (n_warps < kMaxScanWarps && groups * n_warps * 2 <= (long long)ctx->sm_count * warp_budget) n_warps *= 2;
       // magnitudes the filter's error analysis does not cover select the exact scan (flag read on the device)
       int* range_flag = (int*)(base + o_small + 32);
