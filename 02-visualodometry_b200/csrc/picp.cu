@@ -588,7 +588,6 @@ __global__ void __launch_bounds__(kLinThreads, kCtasPerSm) picp_linearize_kernel
 constexpr int kResThreads = VO_RES_THREADS;
 constexpr int kResWarps = kResThreads / 32;
 constexpr int kResMaxGrid = 160;   // CTAs whose partials one CTA can collect (B200: 148 SMs)
-constexpr int kResBatch = (kResMaxGrid + kResWarps - 1) / kResWarps;  // L2 loads in flight per polling thread
 constexpr int kResMaxQuads = 2816;  // quads per CTA: 5 planes x 2816 x 16 B = 225,280 B of the 232,448 B a CTA can own
 constexpr long long kResSpinLimit = 1ll << 21;  // ~2 s of polling: flag a timeout instead of hanging the GPU
 
@@ -648,7 +647,11 @@ struct RoundCtx {
 // words, collects all CTAs' partials (every CTA on one GPU; CTA 0 only with peers, which then pushes the GPU's sums
 // into every rank's mailbox while every CTA polls its own GPU's mailbox), solves the damped 6x6 system redundantly in
 // every CTA, applies the increment to s_pose and sets *s_stop (0 go on, 1 converged, 2 a wait timed out).
-template <int BAR, int N_THREADS>
+// WARP_SOLVE picks the form of the 6x6 solve (same bits either way, measured with exp/picp_ab.py on a B200): in the
+// resident kernel nothing else runs on the SM while warp 0 solves, and one lane's instruction-level parallelism beats
+// the shuffle latencies of the warp form (6.95 vs 7.43 us per round at 1,048,576); in the streaming kernel the warp
+// form is the faster one (49.7 vs 50.5 us at 10,485,760).
+template <int BAR, int N_THREADS, bool WARP_SOLVE>
 __device__ __forceinline__ void round_exchange_and_solve(const RoundCtx& a, int r, unsigned mb_seq0, VoMailbox* me,
                                                          float (*s_part)[kSlots], double (*s_fin)[kSlots], double* s_tot,
                                                          float* s_pose, float* s_dx, int* s_stop, float& prev_chi) {
@@ -731,17 +734,28 @@ __device__ __forceinline__ void round_exchange_and_solve(const RoundCtx& a, int 
       ok = __all_sync(0xffffffffu, ok);
     }
     s_tot[lane] = tot;
+    float* hb = s_part[0];  // this lane has read its column of s_part for the last time this round: 21 H, 6 b as float
+    hb[lane] = (float)tot;
     __syncwarp();
+    float dx[6];
+    if (WARP_SOLVE) {  // all 32 lanes: six columns of shuffles instead of one lane's chain
+      picp_gn_solve_warp(hb, a.damping, lane, s_dx, dx);
+    } else {  // lane 0 alone (the same bits): shorter when nothing else competes for the scheduler, see the callers
+      if (lane == 0) {
+        float Hu[21], bb[6], x[6];
+#pragma unroll
+        for (int k = 0; k < 21; ++k) Hu[k] = hb[k];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) bb[k] = hb[21 + k];
+        picp_gn_solve(Hu, bb, a.damping, x);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) s_dx[k] = x[k];
+      }
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < 6; ++k) dx[k] = s_dx[k];
+    }
     if (lane == 0) {
-      float Hu[21], bb[6];
-#pragma unroll
-      for (int k = 0; k < 21; ++k) Hu[k] = (float)s_tot[k];
-#pragma unroll
-      for (int k = 0; k < 6; ++k) bb[k] = (float)s_tot[21 + k];
-      float dx[6];
-      picp_gn_solve(Hu, bb, a.damping, dx);
-#pragma unroll
-      for (int k = 0; k < 6; ++k) s_dx[k] = dx[k];
       vo_picp_stats st;
       st.chi_inliers = (float)s_tot[27];
       st.chi_outliers = (float)s_tot[28];
@@ -761,8 +775,7 @@ __device__ __forceinline__ void round_exchange_and_solve(const RoundCtx& a, int 
       }
       *s_stop = stop;
     }
-    __syncwarp();
-    picp_apply_dx_warp(s_dx, s_pose, lane);
+    picp_apply_dx_warp(dx, s_pose, lane);
   }
   named_bar_sync(BAR, N_THREADS);
 }
@@ -864,7 +877,7 @@ __global__ void __launch_bounds__(kResThreads, 1) picp_resident_kernel(const Res
     RoundCtx rc;
     rc.dev = a.dev; rc.ll = a.ll; rc.ll_seq0 = a.ll_seq0; rc.ll_stride = a.ll_stride; rc.damping = a.damping;
     rc.rel_tol = a.rel_tol; rc.peer_n = a.peer_n; rc.peer_rank = a.peer_rank; rc.peers = a.peers;
-    round_exchange_and_solve<0, kResThreads>(rc, r, mb_seq0, me, s_part, s_fin, s_tot, s_pose, s_dx, &s_stop, prev_chi);
+    round_exchange_and_solve<0, kResThreads, false>(rc, r, mb_seq0, me, s_part, s_fin, s_tot, s_pose, s_dx, &s_stop, prev_chi);
     if (s_stop) {
       ++r;
       break;
@@ -1043,7 +1056,7 @@ __global__ void __launch_bounds__(kLinThreads, 1) picp_stream_rounds_kernel(cons
       v[31] = 0.f;
       s_part[warp][lane] = warp_sum32_scatter(v, lane);
     }
-    round_exchange_and_solve<1, kThreads>(rc, r, mb_seq0, me, s_part, s_fin, s_tot, s_pose, s_dx, &s_stop, prev_chi);
+    round_exchange_and_solve<1, kThreads, true>(rc, r, mb_seq0, me, s_part, s_fin, s_tot, s_pose, s_dx, &s_stop, prev_chi);
     if (tid == 0) {
       __threadfence_block();
       *(volatile int*)&s_round_done = r + 1;

@@ -92,14 +92,21 @@ __constant__ float kIdentity12[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
 // frame loop: 0 frame loads, 1 match against the map, 2 PICP rounds, 3 pose + match against the previous frame +
 // anti-join, 4 triangulate + append, 5 initialisation (frames 0/1).  Read with vo_debug_seq_stage_cycles.
 #ifdef VO_SEQ_STAGE_CLOCKS
-__device__ unsigned long long g_seq_stage[8];
-#define VO_SEQ_CLK_DECL long long clk_t = clock64(); unsigned long long clk_acc[6] = {0, 0, 0, 0, 0, 0}
+__device__ unsigned long long g_seq_stage[16];
+#define VO_SEQ_CLK_DECL long long clk_t = clock64(); unsigned long long clk_acc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}
 #define VO_SEQ_CLK(i) do { const long long n_ = clock64(); clk_acc[i] += (unsigned long long)(n_ - clk_t); clk_t = n_; } while (0)
-#define VO_SEQ_CLK_FLUSH do { if (threadIdx.x == 0) for (int i_ = 0; i_ < 6; ++i_) atomicAdd(&g_seq_stage[i_], clk_acc[i_]); } while (0)
+#define VO_SEQ_CLK_FLUSH do { if (threadIdx.x == 0) for (int i_ = 0; i_ < 16; ++i_) atomicAdd(&g_seq_stage[i_], clk_acc[i_]); } while (0)
 #else
 #define VO_SEQ_CLK_DECL do { } while (0)
 #define VO_SEQ_CLK(i) do { } while (0)
 #define VO_SEQ_CLK_FLUSH do { } while (0)
+#endif
+// -DVO_SEQ_ROUND_CLOCKS (with VO_SEQ_STAGE_CLOCKS): thread 0 also splits a Gauss-Newton round: 8 linearize + warp
+// reduction, 9 barrier 1, 10 cross-warp sums + gather to lane 0, 11 6x6 solve + verdict, 12 pose update, 13 barrier 2
+#if defined(VO_SEQ_STAGE_CLOCKS) && defined(VO_SEQ_ROUND_CLOCKS)
+#define VO_SEQ_RCLK(i) VO_SEQ_CLK(i)
+#else
+#define VO_SEQ_RCLK(i) do { } while (0)
 #endif
 
 #ifndef VO_SEQ_MINB
@@ -115,6 +122,7 @@ __global__ void __launch_bounds__(kSeqThreads, VO_SEQ_MINB) seq_pipeline_kernel(
   __shared__ float s_red[2][kSeqWarps][32];
   __shared__ int2 s_verdict[2];
   __shared__ float s_dx[6];
+  __shared__ float s_hb[32];
   __shared__ double s_mom[kSeqWarps][kMom];
   __shared__ float s_pose[12];   // world-in-camera during PICP
   __shared__ float s_prev[12];   // camera-in-world of the previous frame
@@ -333,7 +341,9 @@ __global__ void __launch_bounds__(kSeqThreads, VO_SEQ_MINB) seq_pipeline_kernel(
       // so a warp that runs ahead into the next round never overwrites what a slower warp still has to read.
       const int par = r & 1;
       s_red[par][warp][lane] = mine;
+      VO_SEQ_RCLK(8);
       __syncthreads();
+      VO_SEQ_RCLK(9);
       if (warp == 0) {
         // lane k adds the warps' partials of term k in warp order, in double; lane 0 collects them by shuffle,
         // solves the 6x6 system, and the warp applies the increment (12 pose entries in parallel)
@@ -345,26 +355,24 @@ __global__ void __launch_bounds__(kSeqThreads, VO_SEQ_MINB) seq_pipeline_kernel(
           inl += (int)s_red[par][w][29];
         }
         const float vf = (float)v;
-        float Hu[21], bb[6];
-#pragma unroll
-        for (int k = 0; k < 21; ++k) Hu[k] = __shfl_sync(0xffffffffu, vf, k);
-#pragma unroll
-        for (int k = 0; k < 6; ++k) bb[k] = __shfl_sync(0xffffffffu, vf, 21 + k);
-        const float cur = __shfl_sync(0xffffffffu, vf, 27);
+        s_hb[lane] = vf;  // lane k holds term k: 21 H, 6 b, chi_in, chi_out, ...: through shared memory to the solver
+        __syncwarp();
+        const float cur = s_hb[27];
+        VO_SEQ_RCLK(10);
+        float dx[6];
+        picp_gn_solve_warp(s_hb, a.p.damping, lane, s_dx, dx);
         if (tid == 0) {
-          float dx[6];
-          picp_gn_solve(Hu, bb, a.p.damping, dx);
-#pragma unroll
-          for (int k = 0; k < 6; ++k) s_dx[k] = dx[k];
           const float prev = s_prev_chi;
           const float rel = (prev > 1e-10f) ? __fdiv_rn(fabsf(__fsub_rn(prev, cur)), prev) : 0.f;
           s_prev_chi = cur;
           s_verdict[par] = make_int2((rel < a.p.rel_tol) ? 1 : 0, inl);  // icp_test.cpp:99-106
         }
-        __syncwarp();
-        picp_apply_dx_warp(s_dx, s_pose, lane);
+        VO_SEQ_RCLK(11);
+        picp_apply_dx_warp(dx, s_pose, lane);
+        VO_SEQ_RCLK(12);
       }
       __syncthreads();
+      VO_SEQ_RCLK(13);
       rounds_done = r + 1;
       const int2 verdict = s_verdict[par];
       last_inl = verdict.y;
@@ -438,11 +446,11 @@ __global__ void __launch_bounds__(kSeqThreads, VO_SEQ_MINB) seq_pipeline_kernel(
 }  // namespace
 
 #ifdef VO_SEQ_STAGE_CLOCKS
-extern "C" int vo_debug_seq_stage_cycles(unsigned long long out[8], int reset) {
-  if (cudaMemcpyFromSymbol(out, g_seq_stage, 64) != cudaSuccess) return VO_ERR_CUDA;
+extern "C" int vo_debug_seq_stage_cycles(unsigned long long out[16], int reset) {
+  if (cudaMemcpyFromSymbol(out, g_seq_stage, 128) != cudaSuccess) return VO_ERR_CUDA;
   if (reset) {
-    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (cudaMemcpyToSymbol(g_seq_stage, z, 64) != cudaSuccess) return VO_ERR_CUDA;
+    unsigned long long z[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (cudaMemcpyToSymbol(g_seq_stage, z, 128) != cudaSuccess) return VO_ERR_CUDA;
   }
   return VO_OK;
 }

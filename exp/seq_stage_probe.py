@@ -22,7 +22,7 @@ def run():
                           wxyz.data_ptr(), wid.data_ptr(), wcnt.data_ptr(), rounds.data_ptr(), None, status.data_ptr())
     ctx.sync()
 run()
-out = (ctypes.c_ulonglong * 8)()
+out = (ctypes.c_ulonglong * 16)()
 lib.vo_debug_seq_stage_cycles(out, 1)
 run()
 lib.vo_debug_seq_stage_cycles(out, 1)
@@ -31,3 +31,11 @@ tot = float(sum(out[:6]))
 print("ok", int((status == 0).sum()), "of", S, "mean rounds/frame", float(rounds[:, 1:].float().mean()))
 for n, c in zip(names, out[:6]):
     print(f"{n:45s} {100.0 * c / tot:5.1f} %   {c / S / 1e6:8.3f} Mcycles per sequence")
+
+if sum(out[8:14]):
+    rn = ["linearize + warp reduction", "barrier 1", "cross-warp sums + gather to lane 0", "6x6 solve + verdict", "pose update", "barrier 2"]
+    n_rounds = float(rounds[:, 1:].sum())
+    rt = float(sum(out[8:14]))
+    print("Gauss-Newton round split (thread 0), cycles per round:")
+    for n, c in zip(rn, out[8:14]):
+        print(f"  {n:38s} {c / n_rounds:8.0f}  {100.0 * c / rt:5.1f} %")
