@@ -168,6 +168,27 @@ def test_empty_and_invalid_correspondences(ctx):
 
 
 @pytest.mark.parametrize("mode", [1, 2, 3], ids=["stream", "resident", "stream_persistent"])
+@pytest.mark.parametrize("damping", [0.0, 1e-3, 250.0])
+def test_damping_values_track_oracle(ctx, oracle, damping, mode):
+    """H += I * damping (picp_solver.cpp:96): damping 0 takes the pivoted LDLT restatement (one lane, Eigen's
+    algorithm) instead of the unpivoted factorisation every other test runs; small and large damping stay on the
+    unpivoted one. Every kernel's solve against the oracle's, 6 rounds."""
+    n = 20000
+    fr = synth.picp_frame(n=n, seed=99)
+    s = _solver(ctx, fr, mode=mode)
+    pose = fr["pose0"].copy()
+    s.enqueue_rounds(3000.0, damping, False, 6)
+    batch = s.fetch_stats(6)
+    for r in range(6):
+        pose, ci, co, ni = oracle.one_round(fr["K"], fr["rows"], fr["cols"], pose, fr["world"], fr["image"], fr["pairs"],
+                                            3000.0, damping, False)
+        assert abs(batch[r].num_inliers - ni) <= (0 if r == 0 else 2), (damping, r)
+        assert abs(batch[r].chi_inliers - ci) <= 2e-4 * max(ci, 1.0), (damping, r)
+    assert np.abs(s.get_pose() - pose).max() <= 2 * POSE_TOL, damping
+    s.close()
+
+
+@pytest.mark.parametrize("mode", [1, 2, 3], ids=["stream", "resident", "stream_persistent"])
 @pytest.mark.parametrize("n,permute,thr,keep,rounds", [(50000, False, 3000.0, False, 10), (50000, True, 100.0, True, 10),
                                                        (120, False, 3000.0, False, 8), (300000, False, 1000.0, False, 5)])
 def test_rounds_track_oracle(ctx, oracle, n, permute, thr, keep, rounds, mode):
