@@ -195,35 +195,53 @@ __device__ __forceinline__ float from_ordered_u32(unsigned u) {
   return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
 }
 
-__global__ void match_minmax10_kernel(const float* __restrict__ A, long long row_begin, long long rows,
-                                      unsigned* __restrict__ mm /* [10] min, [10] max per dimension, ordered */) {
-  unsigned lo[10], hi[10];
-#pragma unroll
-  for (int d = 0; d < 10; ++d) {
-    lo[d] = 0xffffffffu;
-    hi[d] = 0u;
+// Flat, coalesced pass over rows x 10 floats as float2 (a 40-byte row keeps 8-byte alignment): with a grid stride that
+// is a multiple of 5 pairs every thread stays on one pair of dimensions, keeps its four running values in registers
+// and merges them once, through shared-memory atomics, at the end.  (The one-thread-per-row form this replaces read
+// each 128-byte line ten times: 67 us for 42 MB; this one streams.)
+__global__ void __launch_bounds__(256) match_minmax10_kernel(const float* __restrict__ A, long long row_begin, long long rows,
+                                                             unsigned* __restrict__ mm /* [10] min, [10] max per dimension, ordered */) {
+  __shared__ unsigned s_mm[20];
+  if (threadIdx.x < 20) s_mm[threadIdx.x] = threadIdx.x < 10 ? 0xffffffffu : 0u;
+  __syncthreads();
+  const long long n_threads = (long long)gridDim.x * blockDim.x, stride = n_threads - n_threads % 5;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x, n_pairs = rows * 5;
+  const float2* __restrict__ src = reinterpret_cast<const float2*>(A + row_begin * 10);
+  unsigned lo0 = 0xffffffffu, hi0 = 0u, lo1 = 0xffffffffu, hi1 = 0u;
+  auto take = [](float v, unsigned& lo, unsigned& hi) {
+    if (v == v && fabsf(v) <= FLT_MAX) {  // NaN / inf do not stretch the ranges
+      const unsigned u = ordered_u32(v);
+      lo = min(lo, u);
+      hi = max(hi, u);
+    }
+  };
+  if (t < stride) {
+    long long p = t;
+    for (; p + 3 * stride < n_pairs; p += 4 * stride) {  // four loads in flight
+      const float2 v0 = __ldg(src + p), v1 = __ldg(src + p + stride), v2 = __ldg(src + p + 2 * stride), v3 = __ldg(src + p + 3 * stride);
+      take(v0.x, lo0, hi0); take(v0.y, lo1, hi1);
+      take(v1.x, lo0, hi0); take(v1.y, lo1, hi1);
+      take(v2.x, lo0, hi0); take(v2.y, lo1, hi1);
+      take(v3.x, lo0, hi0); take(v3.y, lo1, hi1);
+    }
+    for (; p < n_pairs; p += stride) {
+      const float2 v = __ldg(src + p);
+      take(v.x, lo0, hi0);
+      take(v.y, lo1, hi1);
+    }
+    const int d = 2 * (int)(t % 5);
+    if (lo0 <= hi0) {
+      atomicMin(&s_mm[d], lo0);
+      atomicMax(&s_mm[10 + d], hi0);
+    }
+    if (lo1 <= hi1) {
+      atomicMin(&s_mm[d + 1], lo1);
+      atomicMax(&s_mm[11 + d], hi1);
+    }
   }
-  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (long long)gridDim.x * blockDim.x)
-#pragma unroll
-    for (int d = 0; d < 10; ++d) {
-      const float v = __ldg(A + (row_begin + r) * 10 + d);
-      if (v == v && fabsf(v) <= FLT_MAX) {  // NaN / inf do not stretch the ranges
-        const unsigned u = ordered_u32(v);
-        lo[d] = min(lo[d], u);
-        hi[d] = max(hi[d], u);
-      }
-    }
-#pragma unroll
-  for (int d = 0; d < 10; ++d) {
-    for (int o = 16; o > 0; o >>= 1) {
-      lo[d] = min(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], o));
-      hi[d] = max(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], o));
-    }
-    if ((threadIdx.x & 31) == 0) {
-      atomicMin(&mm[d], lo[d]);
-      atomicMax(&mm[10 + d], hi[d]);
-    }
-  }
+  __syncthreads();
+  if (threadIdx.x < 10) atomicMin(&mm[threadIdx.x], s_mm[threadIdx.x]);
+  else if (threadIdx.x < 20) atomicMax(&mm[threadIdx.x], s_mm[threadIdx.x]);
 }
 
 // midpoint of dimension k's finite range over rows and columns: the filter works on centred descriptors
@@ -242,10 +260,26 @@ __device__ __forceinline__ unsigned spread8(unsigned v) {  // abcdefgh -> a000b0
   return v;
 }
 
+// magnitudes (of the centred descriptors) the bf16 filter's error analysis covers; outside them the exact scan runs
+constexpr float kFilterMaxAbs = 1e15f, kFilterMinAbs = 1e-15f;
+
+// range_flag (nullable): also check the row's ten centred values against the filter's magnitude limits - the keys
+// pass reads the rows anyway (two separate 42 us passes over rows and columns before)
 __global__ void match_keys10_kernel(const float* __restrict__ A, long long row_begin, long long rows,
                                     const unsigned* __restrict__ mm, unsigned* __restrict__ keys,
-                                    unsigned* __restrict__ ids) {
+                                    unsigned* __restrict__ ids, int* __restrict__ range_flag) {
   const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (range_flag) {
+    bool bad = false;
+    if (r < rows) {
+#pragma unroll
+      for (int k = 0; k < 10; ++k) {
+        const float a = fabsf(__ldg(A + (row_begin + r) * 10 + k) - range_center(mm, k));
+        bad |= (a <= FLT_MAX) && ((a > kFilterMaxAbs) || (a != 0.f && a < kFilterMinAbs));
+      }
+    }
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(range_flag, 1);
+  }
   if (r >= rows) return;
   const int dims[4] = {0, 4, 2, 6};
   unsigned key = 0;
@@ -539,7 +573,7 @@ __global__ void __launch_bounds__(32 * kMaxScanWarps, VO_SCAN_MINB) match_scan10
 // 2 |sum a^b^ - sum ab| <= (2^-7 + 2^-16) sum 2|a_k b_k| <= (2^-7 + 2^-16)(|a|^2 + |b|^2); the hi/lo splits (2^-16 each),
 // the fp32 norms, the accumulator and the reference's own float evaluation add less than 2^-14 (|a|^2+|b|^2) together.
 // With eps = 2^-7 + 2^-12 that gives
-//   v < d_reference      for every finite pair whose magnitudes pass match_range_check_kernel (no overflow of the
+//   v < d_reference      for every finite pair whose magnitudes pass the range check of match_keys10_kernel (no overflow of the
 //                        norms, no underflow of the products; otherwise the exact scan above runs instead),
 // (a first version used 2^-8 + 2^-12, taking bf16's unit roundoff for 2^-9: near-duplicate rows, whose rounding errors
 // all point the same way, then lost their true second-best - found by exp/match_stress.py, now tests/test_gpu_match.py)
@@ -549,8 +583,6 @@ __global__ void __launch_bounds__(32 * kMaxScanWarps, VO_SCAN_MINB) match_scan10
 // Columns with v <= bound are marked in a per-row bit mask and evaluated exactly (reference order, fp32) by the
 // row's lane.  NaN/inf rows or columns give v = NaN/inf: never marked, exactly like `d < best` with a NaN/inf d.
 constexpr float kFilterEps = 0.0078125f + 0.000244140625f;  // 2^-7 + 2^-12
-constexpr float kFilterMaxAbs = 1e15f, kFilterMinAbs = 1e-15f;
-
 __device__ __forceinline__ unsigned bf16x2_rn(float lo, float hi) {
   unsigned r;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
@@ -580,16 +612,6 @@ __device__ __forceinline__ void filter_words(const float v[10], bool is_row, uns
   w[5] = is_row ? norm : ones;
   w[6] = is_row ? ones : norm;
   w[7] = is_row ? filter_bound_word(FLT_MAX) : ones;
-}
-
-__global__ void match_range_check_kernel(const float* __restrict__ x, long long n, const unsigned* __restrict__ mm,
-                                         int* __restrict__ flag) {
-  bool bad = false;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const float a = fabsf(__ldg(x + i) - range_center(mm, (int)(i % 10)));
-    bad |= (a <= FLT_MAX) && ((a > kFilterMaxAbs) || (a != 0.f && a < kFilterMinAbs));
-  }
-  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
 }
 
 // per column (sorted position j, padded to whole tiles with NaN): uint2[4], entry t = words (t, t+4) = the
@@ -686,6 +708,7 @@ __device__ __noinline__ Best3 dense_tile_scan(const float* __restrict__ rec, con
 #ifndef VO_MMA_LB
 #define VO_MMA_LB 32 * kMaxScanWarps
 #endif
+template <bool MULTI>  // MULTI: more than one warp per 32-row group (the CTA-wide bound and the final merge)
 __global__ void __launch_bounds__(VO_MMA_LB, 2) match_scan10_mma_kernel(
     const float* __restrict__ A, long long row_begin, long long rows, const unsigned* __restrict__ row_order,
     const unsigned* __restrict__ row_keys_sorted, const float* __restrict__ rec, const int* __restrict__ orig,
@@ -697,6 +720,7 @@ __global__ void __launch_bounds__(VO_MMA_LB, 2) match_scan10_mma_kernel(
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ long long s_t0;
   __shared__ int s_bound[32];
+  __shared__ float s_wbest[kMaxScanWarps][32];  // every warp's best per row (n_warps > 1)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
   const int g = lane >> 2, tq = lane & 3;
   unsigned* sA = reinterpret_cast<unsigned*>(smem_raw);                         // [32 rows][8 words]
@@ -745,6 +769,7 @@ __global__ void __launch_bounds__(VO_MMA_LB, 2) match_scan10_mma_kernel(
     s_t0 = min(a0, n2 - 1) / (kTileRows * kSuper);  // home super-tile
   }
   if (threadIdx.x < 32) s_bound[threadIdx.x] = __float_as_int(FLT_MAX);
+  if (MULTI) s_wbest[warp][lane] = FLT_MAX;
   __syncthreads();
   unsigned afrag[2][4];
 #pragma unroll
@@ -756,6 +781,19 @@ __global__ void __launch_bounds__(VO_MMA_LB, 2) match_scan10_mma_kernel(
   }
   float best = FLT_MAX, second = FLT_MAX, bound = FLT_MAX;
   int idx = -1;
+  // n_warps > 1: the warps scan disjoint column sets, so the second smallest of {every warp's best} U {every warp's
+  // second} is a second-best of the union and bounds every warp's scan - far tighter, early in the walks, than the
+  // smallest published `second` alone (two warps that each hold one near neighbour already pin it).  Stale reads
+  // are only larger, i.e. conservative.
+  auto cta_bound = [&]() {
+    float m1 = FLT_MAX, m2 = FLT_MAX;
+    for (int w = 0; w < n_warps; ++w) {
+      const float b = *(volatile float*)&s_wbest[w][lane];
+      m2 = fminf(m2, fmaxf(m1, b));
+      m1 = fminf(m1, b);
+    }
+    return fminf(m2, __int_as_float(*(volatile int*)&s_bound[lane]));
+  };
   int dense_skip = 0;  // tiles still to be evaluated outright before the filter is probed again (warp-uniform)
   int dense_streak = 0;  // consecutive filtered tiles that turned out dense
   // The rows' bounds ride in the A operand (k = 14,15, held by the threads with tq == 3): the MMA output is v - bound,
@@ -788,9 +826,14 @@ __global__ void __launch_bounds__(VO_MMA_LB, 2) match_scan10_mma_kernel(
   static_assert(kTileRows == 128 && kSuper == 16, "mask words / fragment / box staging assume 128-column tiles, 16 per super-tile");
   const float4* box4 = reinterpret_cast<const float4*>(box);
   const float4* sbox4 = reinterpret_cast<const float4*>(sbox);
-  for (long long step0 = warp; step0 < n_super; step0 += 32ll * n_warps) {
+  // The walk alternates sides of `home` by step parity, so with an even number of warps a fixed residue (step = i *
+  // n_warps + warp) would pin every warp to ONE side, half of them starting a super-tile away from home (2 warps per
+  // group measured slower than 1).  Rotating the residue with i - warp w takes step i * n_warps + ((w + i) mod
+  // n_warps) - lets every warp alternate sides like the single-warp walk; the steps are still covered exactly once.
+  auto my_step = [&](long long i) { return i * n_warps + (MULTI ? ((warp + i) & (n_warps - 1)) : 0); };  // n_warps: power of 2
+  for (long long i0 = 0; i0 * n_warps < n_super; i0 += 32) {
     {  // the next 32 super-tile boxes of this warp's walk
-      const long long st = step0 + (long long)lane * n_warps;
+      const long long st = my_step(i0 + lane);
       float4 lo4 = make_float4(0, 0, 0, 0), hi4 = lo4;
       if (st < n_super) {
         const long long sgl = step_to_super(st);
@@ -803,10 +846,10 @@ __global__ void __launch_bounds__(VO_MMA_LB, 2) match_scan10_mma_kernel(
       __syncwarp();
     }
     for (int si = 0; si < 32; ++si) {
-      const long long step = step0 + (long long)si * n_warps;
+      const long long step = my_step(i0 + si);
       if (step >= n_super) break;
-      if (n_warps > 1) {
-        const float nb = fminf(second, __int_as_float(s_bound[lane]));
+      if (MULTI) {
+        const float nb = fminf(second, cta_bound());
         if (__any_sync(0xffffffffu, nb < bound)) {
           bound = nb;
           refresh_thr();
@@ -945,15 +988,16 @@ __global__ void __launch_bounds__(VO_MMA_LB, 2) match_scan10_mma_kernel(
           bound = fminf(bound, second);
         }
         __syncwarp();
-        if (n_warps > 1) {
+        if (MULTI) {
+          s_wbest[warp][lane] = best;
           if (second < FLT_MAX) atomicMin(&s_bound[lane], __float_as_int(second));  // second >= 0: int order = float order
-          bound = fminf(bound, __int_as_float(s_bound[lane]));
+          bound = fminf(bound, cta_bound());
         }
         refresh_thr();
       }
     }
   }
-  if (n_warps > 1) {
+  if (MULTI) {
     __syncthreads();
     float* m_best = reinterpret_cast<float*>(smem_raw);
     float* m_second = m_best + 32 * n_warps;
@@ -1322,11 +1366,13 @@ int match_dev_impl(vo_ctx* ctx, const float* d_descA, int64_t n1, const float* d
       match_minmax10_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(d_descB, 0, n2, mm);
       VO_CHECK_LAUNCH(ctx, "match_minmax10_kernel");
     }
-    match_keys10_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, ctx->stream>>>(d_descA, row_begin, rows, mm, keys, ids);
+    int* range_flag = (int*)(base + o_small + 32);  // (zeroed with d_total above)
+    match_keys10_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, ctx->stream>>>(d_descA, row_begin, rows, mm, keys, ids,
+                                                                                 indexed ? range_flag : nullptr);
     VO_CHECK_LAUNCH(ctx, "match_keys10_kernel");
     VO_CUDA(ctx, cub::DeviceRadixSort::SortPairs(base + o_sorttmp, sort_tmp_bytes, keys, keys2, ids, sorted_ids,
                                                  (int)rows, 0, 32, ctx->stream));
-    ctx->launches += 4;  // CUB's histogram + onesweep passes
+    ctx->launches += 6;  // CUB's histogram + exclusive sum + four onesweep passes
     order = sorted_ids;
     if (indexed) {
       unsigned* ckeys = (unsigned*)(base + o_ckeys);
@@ -1336,11 +1382,11 @@ int match_dev_impl(vo_ctx* ctx, const float* d_descA, int64_t n1, const float* d
       float* rec = (float*)(base + o_rec);
       int* orig = (int*)(base + o_orig);
       float* box = (float*)(base + o_box);
-      match_keys10_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, ctx->stream>>>(d_descB, 0, n2, mm, ckeys, cids);
+      match_keys10_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, ctx->stream>>>(d_descB, 0, n2, mm, ckeys, cids, range_flag);
       VO_CHECK_LAUNCH(ctx, "match_keys10_kernel");
       VO_CUDA(ctx, cub::DeviceRadixSort::SortPairs(base + o_sorttmp, sort_tmp_bytes, ckeys, ckeys2, cids, corder, (int)n2, 0,
                                                    32, ctx->stream));
-      ctx->launches += 4;
+      ctx->launches += 6;
       match_gather10_kernel<<<(unsigned)((n2p + 255) / 256), 256, 0, ctx->stream>>>(d_descB, corder, n2, rec, orig);
       VO_CHECK_LAUNCH(ctx, "match_gather10_kernel");
       match_tilebox10_kernel<<<(unsigned)n_tiles, kTileRows, 0, ctx->stream>>>(rec, n2, box);
@@ -1355,21 +1401,24 @@ int match_dev_impl(vo_ctx* ctx, const float* d_descA, int64_t n1, const float* d
       // warps per 32-row group: enough to give every SM ~32 warps when the rows alone cannot
       const long long groups = (seg_rows + 31) / 32;
       int n_warps = 1;
-      // measured (exp/match_mid.py, rows x 1M columns): 64 resident warps per SM pay from ~2048 row groups on
-      // (65536 rows 2.38 -> 2.28 ms, 131072 rows 3.75 -> 3.45 ms), 32 are better below (16384 rows 1.27 vs 1.34 ms)
+      // measured (exp/match_nwarps.py, rows x 1M columns, B200; ms with 1 / 2 / 4 / 8 / 16 warps per group):
+      //   2048 rows 2.99 1.85 1.12 0.79 0.66 | 16384 rows 2.71 1.81 1.20 1.05 1.05 | 65536 rows 2.97 2.42 2.04 1.97 2.35
+      //   131072 rows (one of 8 curve shards) 3.13 2.93 2.70 2.91 | 262144 (one of 4) 4.75 4.83 4.61 5.22
+      //   524288 (one of 2) 8.16 8.80 8.59 9.91 | 1048576 14.90 16.71
       static const long long env_budget = getenv("VO_MATCH_WARP_BUDGET") ? atoll(getenv("VO_MATCH_WARP_BUDGET")) : 0;
-      // (round 2, 64-register kernel: 131072 rows 3.70 ms at a budget of 64, 3.55 ms at 128, 3.92 ms at 256)
-      const long long warp_budget = env_budget > 0 ? env_budget : (groups >= 4096 ? 128 : (groups >= 2048 ? 64 : 32));
-      while (n_warps < kMaxScanWarps && groups * n_warps * 2 <= (long long)ctx->sm_count * warp_budget) n_warps *= 2;
+      if (groups >= 16384 && env_budget <= 0) {
+        n_warps = 1;
+      } else if (groups >= 4096 && env_budget <= 0) {
+        n_warps = 4;
+      } else {
+        const long long warp_budget = env_budget > 0 ? env_budget : (groups >= 2048 ? 64 : 32);
+        while (n_warps < kMaxScanWarps && groups * n_warps * 2 <= (long long)ctx->sm_count * warp_budget) n_warps *= 2;
+      }
+      if (const char* e = getenv("VO_MATCH_NWARPS")) n_warps = max(1, min(kMaxScanWarps, atoi(e)));  // experiments
       // magnitudes the filter's error analysis does not cover select the exact scan (flag read on the device)
-      int* range_flag = (int*)(base + o_small + 32);
       static const bool env_exact = getenv("VO_MATCH_FORCE_EXACT") != nullptr;  // diagnostics: skip the filter
       const bool force_exact = env_exact || path == VO_MATCH_PATH_INDEXED_EXACT;
       if (force_exact) VO_CUDA(ctx, cudaMemsetAsync(range_flag, 1, 4, ctx->stream));
-      match_range_check_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(d_descA + row_begin * 10, rows * 10, mm, range_flag);
-      VO_CHECK_LAUNCH(ctx, "match_range_check_kernel");
-      match_range_check_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(d_descB, n2 * 10, mm, range_flag);
-      VO_CHECK_LAUNCH(ctx, "match_range_check_kernel");
       uint2* frag = (uint2*)(base + o_frag);
       match_gatherfrag10_kernel<<<(unsigned)((n_tiles * kTileRows + 255) / 256), 256, 0, ctx->stream>>>(
           d_descB, corder, n2, n_tiles * kTileRows, mm, (uint4*)frag);
@@ -1377,10 +1426,11 @@ int match_dev_impl(vo_ctx* ctx, const float* d_descA, int64_t n1, const float* d
       const size_t mma_smem = 1024 + (size_t)n_warps * kMmaWarpSmem;
       static_assert(kMmaWarpSmem >= 3 * 32 * 4, "merge arrays reuse the fragment / mask buffers");
       if (mma_smem > 48 * 1024)
-        VO_CUDA(ctx, cudaFuncSetAttribute(match_scan10_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        VO_CUDA(ctx, cudaFuncSetAttribute(match_scan10_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           1024 + kMaxScanWarps * kMmaWarpSmem));
+      auto mma_scan = n_warps > 1 ? match_scan10_mma_kernel<true> : match_scan10_mma_kernel<false>;
       if (groups > 0)
-      match_scan10_mma_kernel<<<(unsigned)groups, 32 * n_warps, mma_smem, ctx->stream>>>(
+      mma_scan<<<(unsigned)groups, 32 * n_warps, mma_smem, ctx->stream>>>(
           d_descA, row_begin, seg_rows, sorted_ids + seg_lo, keys2 + seg_lo, rec, orig, frag, box, sbox, ckeys2, n2, mm,
           range_flag, pb, ps, pi);
       VO_CHECK_LAUNCH(ctx, "match_scan10_mma_kernel");
@@ -1407,16 +1457,22 @@ int match_dev_impl(vo_ctx* ctx, const float* d_descA, int64_t n1, const float* d
                                                                       ratio_thr, d_best, d_second, idx, flags,
                                                                       counts);
   VO_CHECK_LAUNCH(ctx, "match_merge_kernel");
+  if (d_match_idx) {
+    match_idx_kernel<<<(unsigned)merge_blocks, 256, 0, ctx->stream>>>(flags, idx, rows, d_match_idx);
+    VO_CHECK_LAUNCH(ctx, "match_idx_kernel");
+    // the sharded path wants the per-row result only (it compacts after the exchange): no pair list, no count, and
+    // no host synchronisation between the scan and the all-reduce
+    if (!d_pairs_out && capacity == 0 && !stats && !want_ids) {
+      if (n_out) *n_out = 0;
+      return VO_OK;
+    }
+  }
   st = vo_scan_block_counts(ctx, counts, merge_blocks, d_total);
   if (st) return st;
   match_scatter_kernel<<<(unsigned)merge_blocks, 256, 0, ctx->stream>>>(
       flags, idx, counts, rows, row_begin, capacity, want_ids ? d_idA : nullptr, want_ids ? d_idB : nullptr,
       reinterpret_cast<int2*>(d_pairs_out), d_correct);
   VO_CHECK_LAUNCH(ctx, "match_scatter_kernel");
-  if (d_match_idx) {
-    match_idx_kernel<<<(unsigned)merge_blocks, 256, 0, ctx->stream>>>(flags, idx, rows, d_match_idx);
-    VO_CHECK_LAUNCH(ctx, "match_idx_kernel");
-  }
   if (want_ids && n2 > 0) {
     VO_CUDA(ctx, cudaMemsetAsync(table, 0xFF, (size_t)table_size * 8, ctx->stream));
     idjoin_build_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, ctx->stream>>>(d_idB, n2, table, table_size - 1);
