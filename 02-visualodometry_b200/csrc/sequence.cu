@@ -112,7 +112,11 @@ __device__ unsigned long long g_seq_stage[16];
 #ifndef VO_SEQ_MINB
 #define VO_SEQ_MINB 6
 #endif
-__global__ void __launch_bounds__(kSeqThreads, VO_SEQ_MINB) seq_pipeline_kernel(const SeqArgs a) {
+// MINB = resident CTAs per SM the register allocation is sized for: 6 (80 registers) for throughput when the batch fills
+// the machine; 4 (128 registers, a third of the spills) when there are fewer sequences than resident slots anyway and
+// only one sequence's latency counts (measured round 2: 512 sequences 12.8 -> 12.2 ms, 4096 sequences 64.2 -> 67.6 ms).
+template <int MINB>
+__global__ void __launch_bounds__(kSeqThreads, MINB) seq_pipeline_kernel(const SeqArgs a) {
   __shared__ FrameBuf s_curr, s_next;
   __shared__ __align__(16) float s_tile[kSeqThreads * kDimPad];  // map descriptors, 128 rows at a time
   __shared__ int2 s_iw[kSeqThreads];                              // (image idx in next, world idx)
@@ -482,7 +486,10 @@ int vo_seq_batch_run_dev(vo_ctx* ctx, const vo_seq_params* params, int n_seq, in
   a.cnt = d_cnt; a.uv = d_uv; a.desc = d_desc; a.id_real = d_id_real;
   a.poses = d_poses; a.w_xyz = d_world_xyz; a.w_desc = (float*)base; a.w_id = d_world_id; a.w_cnt = d_world_cnt;
   a.rounds = d_rounds; a.inliers = d_inliers; a.status = d_status;
-  seq_pipeline_kernel<<<(unsigned)n_seq, kSeqThreads, 0, ctx->stream>>>(a);
+  if (n_seq <= (long long)ctx->sm_count * 4)
+    seq_pipeline_kernel<4><<<(unsigned)n_seq, kSeqThreads, 0, ctx->stream>>>(a);
+  else
+    seq_pipeline_kernel<VO_SEQ_MINB><<<(unsigned)n_seq, kSeqThreads, 0, ctx->stream>>>(a);
   VO_CHECK_LAUNCH(ctx, "seq_pipeline_kernel");
   return VO_OK;
 }
