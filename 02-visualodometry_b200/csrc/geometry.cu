@@ -328,6 +328,8 @@ int vo_triangulate_dev(vo_ctx* ctx, const float K[9], const float T1[12], const 
   VO_REQUIRE(ctx, K && T1 && T2 && n >= 0, "vo_triangulate: arguments");
   if (n == 0) return VO_OK;  // cam.cpp:103-106: nothing to do
   VO_REQUIRE(ctx, d_x1 && d_x2 && d_xyz_out, "vo_triangulate: null buffers");
+  VO_REQUIRE(ctx, ((reinterpret_cast<uintptr_t>(d_x1) | reinterpret_cast<uintptr_t>(d_x2)) & 7u) == 0,
+             "vo_triangulate_dev: d_x1 / d_x2 must be 8-byte aligned");  // read as float2
   ProjPair pp;
   projection_matrix(K, T1, pp.P1);
   projection_matrix(K, T2, pp.P2);

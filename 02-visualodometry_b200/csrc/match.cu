@@ -215,7 +215,18 @@ __global__ void __launch_bounds__(256) match_minmax10_kernel(const float* __rest
       hi = max(hi, u);
     }
   };
-  if (t < stride) {
+  if ((reinterpret_cast<unsigned long long>(src) & 7ull) != 0) {  // a caller's view at an odd float offset: scalar loads
+    const long long stride1 = n_threads - n_threads % 10, n_vals = rows * 10;
+    if (t < stride1) {
+      const float* __restrict__ s1 = A + row_begin * 10;
+      for (long long p = t; p < n_vals; p += stride1) take(__ldg(s1 + p), lo0, hi0);
+      const int d = (int)(t % 10);
+      if (lo0 <= hi0) {
+        atomicMin(&s_mm[d], lo0);
+        atomicMax(&s_mm[10 + d], hi0);
+      }
+    }
+  } else if (t < stride) {
     long long p = t;
     for (; p + 3 * stride < n_pairs; p += 4 * stride) {  // four loads in flight
       const float2 v0 = __ldg(src + p), v1 = __ldg(src + p + stride), v2 = __ldg(src + p + 2 * stride), v3 = __ldg(src + p + 3 * stride);

@@ -1598,6 +1598,8 @@ int vo_picp_set_points(vo_picp* s, const float* world_xyz, int64_t n_world, cons
 int vo_picp_set_points_dev(vo_picp* s, const float* d_world_xyz, int64_t n_world, const float* d_image_xy,
                            int64_t n_image) {
   if (!s || n_world < 0 || n_image < 0 || !d_world_xyz || !d_image_xy) return VO_ERR_INVALID;
+  if ((reinterpret_cast<uintptr_t>(d_image_xy) & 7u) != 0)  // read as float2 (include/vo_b200.h, conventions)
+    return vo_set_error(s->ctx, VO_ERR_INVALID, "vo_picp_set_points_dev", "d_image_xy must be 8-byte aligned");
   int st = vo_ctx_activate(s->ctx);  // the frees below must run on this context's device
   if (st) return st;
   if (s->own_points) {
@@ -1620,6 +1622,8 @@ int vo_picp_set_correspondences_dev(vo_picp* s, const int32_t* d_pairs, int64_t 
   if (!s || n_pairs < 0 || (n_pairs && !d_pairs)) return VO_ERR_INVALID;
   vo_ctx* ctx = s->ctx;
   if (!s->d_world || !s->d_image) return vo_set_error(ctx, VO_ERR_STATE, "picp", "set_points not called");
+  if ((reinterpret_cast<uintptr_t>(d_pairs) & 7u) != 0)  // read as int2
+    return vo_set_error(ctx, VO_ERR_INVALID, "vo_picp_set_correspondences_dev", "d_pairs must be 8-byte aligned");
   int st = vo_ctx_activate(ctx);
   if (st) return st;
   // Nothing is gathered here: the resident kernel gathers straight into shared memory, the streaming kernel

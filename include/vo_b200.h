@@ -17,6 +17,9 @@
  *   - functions without a suffix take HOST buffers and return finished host-visible results
  *     (the reference is synchronous); `_dev` variants take DEVICE pointers resident in HBM
  *     and only enqueue work on the context's stream unless stated otherwise.
+ *   - alignment of DEVICE arrays: 2-vectors (image points, int32 pairs) are read as 8-byte words and must be 8-byte
+ *     aligned - any cudaMalloc'd buffer, or an element-aligned view into one, is; misaligned pointers are rejected with
+ *     VO_ERR_INVALID.  float[3] points and descriptor rows need only their natural 4-byte alignment.
  *   - a vo_ctx is bound to one GPU and one CUDA stream; handles are not thread-safe.
  *   - there is no CPU fallback: every call fails with VO_ERR_CUDA when no device is usable.
  */

@@ -131,6 +131,33 @@ def test_match_indexed_path_offset_descriptors(ctx, oracle):
     assert np.array_equal(p2, rp)
 
 
+def test_match_indexed_path_descriptors_at_odd_float_offsets(ctx, oracle):
+    """device pointers that are only 4-byte aligned (views into a larger float buffer at odd offsets, with a row
+    offset on top): the index build's vectorised passes must not assume more than the C-ABI promises"""
+    import torch
+    A, B = synth.descriptors(9000, 10000, seed=5, copy_frac=0.8, dup_frac=0.01, noise=0.03)
+    rp, _, rbest, rsecond, ridx = oracle.match(A, B, want_rows=True, n_threads=8)
+    bufA = torch.zeros(A.size + 3, dtype=torch.float32, device="cuda")
+    bufB = torch.zeros(B.size + 5, dtype=torch.float32, device="cuda")
+    bufA[1:1 + A.size] = torch.from_numpy(A.ravel()).cuda()
+    bufB[3:3 + B.size] = torch.from_numpy(B.ravel()).cuda()
+    pA, pB = bufA.data_ptr() + 4, bufB.data_ptr() + 12
+    assert pA % 8 == 4 and pB % 8 == 4
+    for row_begin, row_end in ((0, len(A)), (301, len(A))):
+        rows = row_end - row_begin
+        best = torch.empty(rows, dtype=torch.float32, device="cuda")
+        second = torch.empty_like(best)
+        idx = torch.empty(rows, dtype=torch.int32, device="cuda")
+        pairs = torch.empty((rows, 2), dtype=torch.int32, device="cuda")
+        n, _ = ctx.match_dev(pA, len(A), pB, len(B), 10, pairs.data_ptr(), rows, row_begin=row_begin, row_end=row_end,
+                             d_best=best.data_ptr(), d_second=second.data_ptr(), d_idx=idx.data_ptr())
+        torch.cuda.synchronize()
+        assert np.array_equal(idx.cpu().numpy(), ridx[row_begin:row_end])
+        assert np.array_equal(best.cpu().numpy().view(np.uint32), rbest[row_begin:row_end].view(np.uint32))
+        assert np.array_equal(second.cpu().numpy().view(np.uint32), rsecond[row_begin:row_end].view(np.uint32))
+        assert np.array_equal(pairs[:n].cpu().numpy(), rp[rp[:, 0] >= row_begin])
+
+
 def test_match_indexed_path_nonfinite(ctx, oracle):
     """NaN / inf descriptors inside the indexed path: a NaN or inf distance never wins (`d < best` is false),
     on the filter exactly as in the reference loop"""
