@@ -118,15 +118,42 @@ __device__ __forceinline__ f2 rcp2_newton(f2 z, float z0, float z1) {
   return fma2(r, fma2(z, pack2(-r0, -r1), pack2(1.f, 1.f)), r);
 }
 
-// Two correspondences: exact part per point, then J, H += lambda J^T J and b += lambda J^T e in packed
-// f32x2 (lane 0 = first point, lane 1 = second; acc2[k] holds the two lanes' partial sums of slot k).
-// Points that do not contribute get all-zero Jacobian rows instead of a branch.
-// state of a pair between the three stages below
+// Four correspondences (one quad = two packed pairs) per call: the exact part per point, then J, H += lambda J^T J
+// and b += lambda J^T e in packed f32x2 (lane 0 = first point of a pair, lane 1 = second; acc2[k] holds the two
+// lanes' partial sums of slot k).  Points that do not contribute get all-zero Jacobian rows instead of a branch.
+//
+// Instruction budget (the kernels are bound by FP32 / ALU issue, not by HBM: profiles/r02_picp_*): everything stays
+// packed from the shared-memory load to the accumulators, and the select / compare / integer work is kept off the
+// common path:
+//  * a dropped point is removed by zeroing its 1/z ALONE - every Jacobian entry carries a factor 1/z, so J = 0
+//    exactly provided the point's c, q and e are finite.  `odd` collects the pairs for which that is not certain
+//    (|c0 + c1 + c2| or chi not finite - conservative: a sum may overflow where no term does); such a quad takes the
+//    accumulation that zeroes every input of a dropped point by select (the semantics of the first version).
+//  * no negated copies of c: the pinhole Jacobian is built from -g, -h and -fx/z, which turns columns 2 and 3 of BOTH
+//    rows into their exact negatives; round-to-nearest is sign-symmetric, so the affected sums (H[i][j] with exactly
+//    one index in {2,3}; b[2], b[3]) are the exact negatives of the true ones and are flipped back once per round
+//    where the packed accumulators are unpacked (picp_slot_sign).
+//  * the inlier / outlier counters are predicated adds, chi sums are plain packed adds of the selected chi.
 struct PairState {
-  PointTerms t0, t1;
-  f2 c0, c1, c2, q0, q1, iz;
+  f2 c0, c1, c2, q0, q1, iz, e0, e1, chi;
   bool fix0, fix1;  // this lane needs the reference's arithmetic verbatim (general K, IEEE reciprocal)
+  bool odd;         // some term of the pair may be non-finite: dropped points need every input zeroed
+  bool use0, use1, out0, out1;
 };
+
+// sign of accumulator slot k (0..20 upper-triangular H row by row, 21..26 b) in the column-flipped pinhole form
+__host__ __device__ constexpr bool picp_slot_flipped(int k) {
+  if (k >= 27) return false;
+  if (k >= 21) return k - 21 == 2 || k - 21 == 3;
+  int i = 0, first = 0;
+  while (k >= first + (6 - i)) { first += 6 - i; ++i; }
+  const int j = i + (k - first);
+  return ((i == 2 || i == 3) != (j == 2 || j == 3));
+}
+
+__device__ __forceinline__ void count_if(int& n, bool p) {
+  asm("{\n.reg .pred q;\nsetp.ne.u32 q, %1, 0;\n@q add.s32 %0, %0, 1;\n}" : "+r"(n) : "r"((unsigned)p));
+}
 
 // stage 1: c = R p + t and the pinhole shortcut values of q and 1/z for both lanes
 template <bool PINHOLE>
@@ -137,105 +164,123 @@ __device__ __forceinline__ void pair_front(const PicpCam& cam, const float* __re
   s.c0 = add2(bc(T[3]), add2(prod2(bc(T[0]), px), add2(prod2(bc(T[1]), py), prod2(bc(T[2]), pz))));
   s.c1 = add2(bc(T[7]), add2(prod2(bc(T[4]), px), add2(prod2(bc(T[5]), py), prod2(bc(T[6]), pz))));
   s.c2 = add2(bc(T[11]), add2(prod2(bc(T[8]), px), add2(prod2(bc(T[9]), py), prod2(bc(T[10]), pz))));
-  unpack2(s.c0, s.t0.c0, s.t1.c0);
-  unpack2(s.c1, s.t0.c1, s.t1.c1);
-  unpack2(s.c2, s.t0.c2, s.t1.c2);
+  float z0, z1, f0, f1;
+  unpack2(s.c2, z0, z1);
+  unpack2(add2(add2(s.c0, s.c1), s.c2), f0, f1);  // finite <=> c0, c1, c2 all finite (and their sum does not overflow)
+  const bool fin0 = finite_f(f0), fin1 = finite_f(f1);
   s.q0 = 0ull; s.q1 = 0ull; s.iz = 0ull;
   if (PINHOLE) {  // shortcut values for both lanes (see picp_project<> for why they are exact)
     s.q0 = add2(prod2(bc(cam.K[0]), s.c0), prod2(bc(cam.K[2]), s.c2));
     s.q1 = add2(prod2(bc(cam.K[4]), s.c1), prod2(bc(cam.K[5]), s.c2));
-    s.iz = rcp2_newton(s.c2, s.t0.c2, s.t1.c2);
+    s.iz = rcp2_newton(s.c2, z0, z1);
   }
-  unpack2(s.q0, s.t0.q0, s.t1.q0);
-  unpack2(s.q1, s.t0.q1, s.t1.q1);
-  unpack2(s.iz, s.t0.iz, s.t1.iz);
-  const bool sc0 = PINHOLE && (s.t0.c2 >= 1e-30f) && (s.t0.c2 <= 1e30f) && finite_f(s.t0.c0) && finite_f(s.t0.c1);
-  const bool sc1 = PINHOLE && (s.t1.c2 >= 1e-30f) && (s.t1.c2 <= 1e30f) && finite_f(s.t1.c0) && finite_f(s.t1.c1);
-  s.fix0 = !sc0 && !(s.t0.c2 <= 0.f);
-  s.fix1 = !sc1 && !(s.t1.c2 <= 0.f);
+  const bool sc0 = PINHOLE && fin0 && (z0 >= 1e-30f) && (z0 <= 1e30f);
+  const bool sc1 = PINHOLE && fin1 && (z1 >= 1e-30f) && (z1 <= 1e30f);
+  s.fix0 = !sc0 && !(z0 <= 0.f);
+  s.fix1 = !sc1 && !(z1 <= 0.f);
+  s.odd = !fin0 || !fin1;
 }
 
 // stage 2 (rare): the reference's arithmetic verbatim for the lanes that need it
 __device__ __forceinline__ void pair_fix(const PicpCam& cam, PairState& s) {
+  float c00, c01, c10, c11, c20, c21, q00, q01, q10, q11, iz0, iz1;
+  unpack2(s.c0, c00, c01);
+  unpack2(s.c1, c10, c11);
+  unpack2(s.c2, c20, c21);
+  unpack2(s.q0, q00, q01);
+  unpack2(s.q1, q10, q11);
+  unpack2(s.iz, iz0, iz1);
   if (s.fix0) {
-    s.t0.q0 = dot3_rn(cam.K[0], s.t0.c0, cam.K[1], s.t0.c1, cam.K[2], s.t0.c2);
-    s.t0.q1 = dot3_rn(cam.K[3], s.t0.c0, cam.K[4], s.t0.c1, cam.K[5], s.t0.c2);
-    s.t0.iz = __frcp_rn(dot3_rn(cam.K[6], s.t0.c0, cam.K[7], s.t0.c1, cam.K[8], s.t0.c2));
+    q00 = dot3_rn(cam.K[0], c00, cam.K[1], c10, cam.K[2], c20);
+    q10 = dot3_rn(cam.K[3], c00, cam.K[4], c10, cam.K[5], c20);
+    iz0 = __frcp_rn(dot3_rn(cam.K[6], c00, cam.K[7], c10, cam.K[8], c20));
   }
   if (s.fix1) {
-    s.t1.q0 = dot3_rn(cam.K[0], s.t1.c0, cam.K[1], s.t1.c1, cam.K[2], s.t1.c2);
-    s.t1.q1 = dot3_rn(cam.K[3], s.t1.c0, cam.K[4], s.t1.c1, cam.K[5], s.t1.c2);
-    s.t1.iz = __frcp_rn(dot3_rn(cam.K[6], s.t1.c0, cam.K[7], s.t1.c1, cam.K[8], s.t1.c2));
+    q01 = dot3_rn(cam.K[0], c01, cam.K[1], c11, cam.K[2], c21);
+    q11 = dot3_rn(cam.K[3], c01, cam.K[4], c11, cam.K[5], c21);
+    iz1 = __frcp_rn(dot3_rn(cam.K[6], c01, cam.K[7], c11, cam.K[8], c21));
   }
-  s.q0 = pack2(s.t0.q0, s.t1.q0);
-  s.q1 = pack2(s.t0.q1, s.t1.q1);
-  s.iz = pack2(s.t0.iz, s.t1.iz);
+  s.q0 = pack2(q00, q01);
+  s.q1 = pack2(q10, q11);
+  s.iz = pack2(iz0, iz1);
 }
 
-// stage 3: u, inside test, error, chi, status; then J, H += lambda J^T J and b += lambda J^T e
-template <bool KEEP, bool PINHOLE>
-__device__ __forceinline__ void pair_back(const PicpCam& cam, float thr, PairState& s, float zu0, float zv0, float zu1,
-                                          float zv1, bool v0, bool v1, f2 (&acc2)[29], int& n_in, int& n_out, int& st0,
-                                          int& st1) {
-  PointTerms& t0 = s.t0;
-  PointTerms& t1 = s.t1;
-  {
-    const f2 q0 = s.q0, q1 = s.q1, iz = s.iz;
-    const f2 u = prod2(q0, iz), v = prod2(q1, iz);
-    float u0, u1, w0, w1;
-    unpack2(u, u0, u1);
-    unpack2(v, w0, w1);
-    // camera.h:27,31-34 with their NaN behaviour: a NaN compares false and stays "inside"
-    const bool ins0 = v0 && !(t0.c2 <= 0.f) && !(u0 < 0.f) && !(u0 > cam.umax) && !(w0 < 0.f) && !(w0 > cam.vmax);
-    const bool ins1 = v1 && !(t1.c2 <= 0.f) && !(u1 < 0.f) && !(u1 > cam.umax) && !(w1 < 0.f) && !(w1 > cam.vmax);
-    const f2 e0 = sub2(u, pack2(zu0, zu1)), e1 = sub2(v, pack2(zv0, zv1));
-    const f2 chi = add2(prod2(e0, e0), prod2(e1, e1));
-    unpack2(e0, t0.e0, t1.e0);
-    unpack2(e1, t0.e1, t1.e1);
-    unpack2(chi, t0.chi, t1.chi);
-    t0.st = ins0 ? ((t0.chi > thr) ? VO_PICP_OUTLIER : VO_PICP_INLIER) : VO_PICP_SKIPPED;
-    t1.st = ins1 ? ((t1.chi > thr) ? VO_PICP_OUTLIER : VO_PICP_INLIER) : VO_PICP_SKIPPED;
-  }
-  st0 = t0.st;
-  st1 = t1.st;
-  const bool in0 = t0.st == VO_PICP_INLIER, in1 = t1.st == VO_PICP_INLIER;
-  const bool out0 = t0.st == VO_PICP_OUTLIER, out1 = t1.st == VO_PICP_OUTLIER;
-  n_in += (int)in0 + (int)in1;
-  n_out += (int)out0 + (int)out1;
-  acc2[27] = fma2(pack2(in0 ? 1.f : 0.f, in1 ? 1.f : 0.f), pack2(in0 ? t0.chi : 0.f, in1 ? t1.chi : 0.f), acc2[27]);
-  acc2[28] = fma2(pack2(out0 ? 1.f : 0.f, out1 ? 1.f : 0.f), pack2(out0 ? t0.chi : 0.f, out1 ? t1.chi : 0.f), acc2[28]);
-  const bool use0 = in0 || (KEEP && out0), use1 = in1 || (KEEP && out1);
-  // contribution weight: 0 (dropped), 1 (inlier) or lambda = sqrt(thr/chi) (kept outlier, picp_solver.cpp:78)
-  float w0 = use0 ? 1.f : 0.f, w1 = use1 ? 1.f : 0.f;
+// stage 3: u, inside test, error, chi, status, counters and chi sums
+template <bool KEEP>
+__device__ __forceinline__ void pair_mid(const PicpCam& cam, float thr, PairState& s, float zu0, float zv0, float zu1,
+                                         float zv1, bool v0, bool v1, f2 (&acc2)[29], int& n_in, int& n_out, int& st0,
+                                         int& st1) {
+  const f2 u = prod2(s.q0, s.iz), v = prod2(s.q1, s.iz);
+  float u0, u1, w0, w1, z0, z1, chi0, chi1;
+  unpack2(u, u0, u1);
+  unpack2(v, w0, w1);
+  unpack2(s.c2, z0, z1);
+  // camera.h:27,31-34 with their NaN behaviour: a NaN compares false and stays "inside"
+  const bool ins0 = v0 && !(z0 <= 0.f) && !(u0 < 0.f) && !(u0 > cam.umax) && !(w0 < 0.f) && !(w0 > cam.vmax);
+  const bool ins1 = v1 && !(z1 <= 0.f) && !(u1 < 0.f) && !(u1 > cam.umax) && !(w1 < 0.f) && !(w1 > cam.vmax);
+  s.e0 = sub2(u, pack2(zu0, zu1));
+  s.e1 = sub2(v, pack2(zv0, zv1));
+  s.chi = add2(prod2(s.e0, s.e0), prod2(s.e1, s.e1));
+  unpack2(s.chi, chi0, chi1);
+  const bool gt0 = chi0 > thr, gt1 = chi1 > thr;
+  const bool in0 = ins0 && !gt0, in1 = ins1 && !gt1;
+  s.out0 = ins0 && gt0;
+  s.out1 = ins1 && gt1;
+  st0 = ins0 ? (gt0 ? VO_PICP_OUTLIER : VO_PICP_INLIER) : VO_PICP_SKIPPED;
+  st1 = ins1 ? (gt1 ? VO_PICP_OUTLIER : VO_PICP_INLIER) : VO_PICP_SKIPPED;
+  count_if(n_in, in0);
+  count_if(n_in, in1);
+  count_if(n_out, s.out0);
+  count_if(n_out, s.out1);
+  acc2[27] = add2(acc2[27], pack2(in0 ? chi0 : 0.f, in1 ? chi1 : 0.f));
+  acc2[28] = add2(acc2[28], pack2(s.out0 ? chi0 : 0.f, s.out1 ? chi1 : 0.f));
+  s.use0 = in0 || (KEEP && s.out0);
+  s.use1 = in1 || (KEEP && s.out1);
+  s.odd = s.odd || !(chi0 <= FLT_MAX) || !(chi1 <= FLT_MAX);  // chi is >= 0, +inf or NaN
+}
+
+// stage 4: J, H += w J^T J and b += w J^T e (tolerance part).  ODD: every input of a dropped point is zeroed.
+template <bool KEEP, bool PINHOLE, bool ODD>
+__device__ __forceinline__ void pair_acc(const PicpCam& cam, float thr, const PairState& s, f2 (&acc2)[29]) {
+  const bool use0 = s.use0, use1 = s.use1;
+  auto keep = [&](f2 x) {
+    if (!ODD) return x;
+    float a, b;
+    unpack2(x, a, b);
+    return pack2(use0 ? a : 0.f, use1 ? b : 0.f);
+  };
+  float iz0, iz1;
+  unpack2(s.iz, iz0, iz1);
+  const f2 iz = pack2(use0 ? iz0 : 0.f, use1 ? iz1 : 0.f);
+  const f2 q0 = keep(s.q0), q1 = keep(s.q1), c0 = keep(s.c0), c1 = keep(s.c1), c2 = keep(s.c2);
+  const f2 e0 = keep(s.e0), e1 = keep(s.e1);
+  // contribution weight: 1 (inlier) or lambda = sqrt(thr/chi) (kept outlier, picp_solver.cpp:78); a dropped point's
+  // weight multiplies zeros
+  f2 w = 0ull;
   if (KEEP) {
-    if (out0) w0 = __fsqrt_rn(__fdiv_rn(thr, t0.chi));
-    if (out1) w1 = __fsqrt_rn(__fdiv_rn(thr, t1.chi));
+    float chi0, chi1;
+    unpack2(s.chi, chi0, chi1);
+    float w0 = (ODD && !use0) ? 0.f : 1.f, w1 = (ODD && !use1) ? 0.f : 1.f;
+    if (s.out0) w0 = __fsqrt_rn(__fdiv_rn(thr, chi0));
+    if (s.out1) w1 = __fsqrt_rn(__fdiv_rn(thr, chi1));
+    w = pack2(w0, w1);
   }
-  // zero the inputs of dropped points so that no inf/NaN of theirs reaches the sums
-  const f2 iz = pack2(use0 ? t0.iz : 0.f, use1 ? t1.iz : 0.f);
-  const f2 nq0 = pack2(use0 ? -t0.q0 : 0.f, use1 ? -t1.q0 : 0.f);
-  const f2 nq1 = pack2(use0 ? -t0.q1 : 0.f, use1 ? -t1.q1 : 0.f);
-  const f2 c0 = pack2(use0 ? t0.c0 : 0.f, use1 ? t1.c0 : 0.f);
-  const f2 c1 = pack2(use0 ? t0.c1 : 0.f, use1 ? t1.c1 : 0.f);
-  const f2 c2 = pack2(use0 ? t0.c2 : 0.f, use1 ? t1.c2 : 0.f);
-  const f2 nc0 = neg2(c0), nc1 = neg2(c1), nc2 = neg2(c2);
-  const f2 e0 = pack2(use0 ? t0.e0 : 0.f, use1 ? t1.e0 : 0.f);
-  const f2 e1 = pack2(use0 ? t0.e1 : 0.f, use1 ? t1.e1 : 0.f);
-  const f2 w = pack2(w0, w1);
-  // ---- tolerance part: J = (Jp*K)*[I | skew(-c)]
+  // ---- J = (Jp*K)*[I | skew(-c)]
   const f2 iz2 = mul2(iz, iz);
-  const f2 m0 = mul2(nq0, iz2), m1 = mul2(nq1, iz2);  // -q*iz^2
+  const f2 p0 = mul2(q0, iz2), p1 = mul2(q1, iz2);  // q*iz^2
   f2 J0[6], J1[6];
   if (PINHOLE) {
-    const f2 fx = pack2(cam.K[0], cam.K[0]), fy = pack2(cam.K[4], cam.K[4]);
-    const f2 cx = pack2(cam.K[2], cam.K[2]), cy = pack2(cam.K[5], cam.K[5]);
-    const f2 a = mul2(iz, fx), d = mul2(iz, fy);
-    const f2 g = fma2(iz, cx, m0), h = fma2(iz, cy, m1);
-    J0[0] = a; J0[1] = 0ull; J0[2] = g;
-    J0[3] = mul2(g, c1); J0[4] = fma2(g, nc0, mul2(a, c2)); J0[5] = mul2(a, nc1);
-    J1[0] = 0ull; J1[1] = d; J1[2] = h;
-    J1[3] = fma2(d, nc2, mul2(h, c1)); J1[4] = mul2(h, nc0); J1[5] = mul2(d, c0);
+    auto bc = [](float x) { return pack2(x, x); };
+    const f2 a = mul2(iz, bc(cam.K[0])), na = mul2(iz, bc(-cam.K[0])), d = mul2(iz, bc(cam.K[4]));
+    const f2 ng = fma2(iz, bc(-cam.K[2]), p0), nh = fma2(iz, bc(-cam.K[5]), p1);  // -(cx/z - q0/z^2), -(cy/z - q1/z^2)
+    // columns 2 and 3 carry the opposite sign in both rows (picp_slot_flipped)
+    J0[0] = a; J0[1] = 0ull; J0[2] = ng;
+    J0[3] = mul2(ng, c1); J0[4] = fma2(ng, c0, mul2(a, c2)); J0[5] = mul2(na, c1);
+    J1[0] = 0ull; J1[1] = d; J1[2] = nh;
+    J1[3] = fma2(d, c2, mul2(nh, c1)); J1[4] = mul2(nh, c0); J1[5] = mul2(d, c0);
   } else {
+    const f2 m0 = neg2(p0), m1 = neg2(p1);
+    const f2 nc0 = neg2(c0), nc1 = neg2(c1), nc2 = neg2(c2);
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
       J0[j] = fma2(iz, pack2(cam.K[j], cam.K[j]), mul2(m0, pack2(cam.K[6 + j], cam.K[6 + j])));
@@ -264,6 +309,41 @@ __device__ __forceinline__ void pair_back(const PicpCam& cam, float thr, PairSta
     if (!z0) acc2[21 + i] = fma2(s0, e0, acc2[21 + i]);
     if (!z1) acc2[21 + i] = fma2(s1, e1, acc2[21 + i]);
   }
+}
+
+// one quad through all stages; v1..v3: validity of points 1..3 (false only in the last quad of a set)
+template <bool KEEP, bool PINHOLE>
+__device__ __forceinline__ void picp_quad(const PicpCam& cam, const float* __restrict__ T, float thr, const float4& wx,
+                                          const float4& wy, const float4& wz, const float4& zu, const float4& zv, bool v1,
+                                          bool v2, bool v3, f2 (&acc2)[29], int& n_in, int& n_out, int& s0, int& s1,
+                                          int& s2, int& s3) {
+  // both pairs of the quad go through the stages together: one (rare) branch each for the verbatim arithmetic and
+  // for the zero-everything accumulation
+  PairState pa, pb;
+  pair_front<PINHOLE>(cam, T, wx.x, wy.x, wz.x, wx.y, wy.y, wz.y, pa);
+  pair_front<PINHOLE>(cam, T, wx.z, wy.z, wz.z, wx.w, wy.w, wz.w, pb);
+  if (pa.fix0 || pa.fix1 || pb.fix0 || pb.fix1) {
+    pair_fix(cam, pa);
+    pair_fix(cam, pb);
+  }
+  pair_mid<KEEP>(cam, thr, pa, zu.x, zv.x, zu.y, zv.y, true, v1, acc2, n_in, n_out, s0, s1);
+  pair_mid<KEEP>(cam, thr, pb, zu.z, zv.z, zu.w, zv.w, v2, v3, acc2, n_in, n_out, s2, s3);
+  if (pa.odd || pb.odd) {
+    pair_acc<KEEP, PINHOLE, true>(cam, thr, pa, acc2);
+    pair_acc<KEEP, PINHOLE, true>(cam, thr, pb, acc2);
+  } else {
+    pair_acc<KEEP, PINHOLE, false>(cam, thr, pa, acc2);
+    pair_acc<KEEP, PINHOLE, false>(cam, thr, pb, acc2);
+  }
+}
+
+// the thread's total of slot i from its packed accumulator (undoing the column flips of the pinhole form)
+template <bool PINHOLE>
+__device__ __forceinline__ float picp_slot_total(const f2 (&acc2)[29], int i) {
+  float lo, hi;
+  unpack2(acc2[i], lo, hi);
+  const float v = lo + hi;
+  return (PINHOLE && picp_slot_flipped(i)) ? -v : v;
 }
 
 // result[32] (double) -> damped solve -> pose update, stats ring, convergence flag. One thread.
@@ -393,7 +473,7 @@ __global__ void __launch_bounds__(kLinThreads, kCtasPerSm) picp_linearize_kernel
   }
   __syncthreads();
 
-  const long long n_tiles = (a.n + kTile - 1) / kTile;
+  const long long n_tiles = (a.n + kTile - 1) / kTile, n_full_tiles = a.n / kTile;
   f2 acc2[29];
 #pragma unroll
   for (int i = 0; i < 29; ++i) acc2[i] = 0ull;
@@ -449,30 +529,32 @@ __global__ void __launch_bounds__(kLinThreads, kCtasPerSm) picp_linearize_kernel
       const float4* tile = reinterpret_cast<const float4*>(s_tiles + (size_t)stage * 5 * kTile);
       const long long base = t * kTile + 4ll * threadIdx.x;
       float4 wx, wy, wz, zu, zv;
-      const bool any = base < a.n;
-      if (any) {
+      int s0, s1, s2, s3;
+      if (t < n_full_tiles) {  // every tile but the last of the stream: no per-point validity
         wx = tile[threadIdx.x];
         wy = tile[kThreads + threadIdx.x];
         wz = tile[2 * kThreads + threadIdx.x];
         zu = tile[3 * kThreads + threadIdx.x];
         zv = tile[4 * kThreads + threadIdx.x];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[stage]);  // values are in registers: hand the stage back
+        picp_quad<KEEP, PINHOLE>(a.cam, T, a.thr, wx, wy, wz, zu, zv, true, true, true, acc2, n_in, n_out, s0, s1, s2, s3);
+      } else {
+        const bool any = base < a.n;
+        if (any) {
+          wx = tile[threadIdx.x];
+          wy = tile[kThreads + threadIdx.x];
+          wz = tile[2 * kThreads + threadIdx.x];
+          zu = tile[3 * kThreads + threadIdx.x];
+          zv = tile[4 * kThreads + threadIdx.x];
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[stage]);
+        if (!any) continue;
+        const long long left = a.n - base;  // >= 1; < 4 only in the last quad of the stream
+        picp_quad<KEEP, PINHOLE>(a.cam, T, a.thr, wx, wy, wz, zu, zv, left > 1, left > 2, left > 3, acc2, n_in, n_out, s0,
+                                 s1, s2, s3);
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty[stage]);  // values are in registers: hand the stage back
-      if (!any) continue;
-      int s0, s1, s2, s3;
-      const long long left = a.n - base;  // >= 1; < 4 only in the last quad of the stream
-      // both pairs of the quad go through the stages together: one (rare) branch for the four points, and the
-      // select-heavy tail of one pair sits in the same basic block as the FFMA2-heavy accumulation of the other
-      PairState pa, pb;
-      pair_front<PINHOLE>(a.cam, T, wx.x, wy.x, wz.x, wx.y, wy.y, wz.y, pa);
-      pair_front<PINHOLE>(a.cam, T, wx.z, wy.z, wz.z, wx.w, wy.w, wz.w, pb);
-      if (pa.fix0 || pa.fix1 || pb.fix0 || pb.fix1) {
-        pair_fix(a.cam, pa);
-        pair_fix(a.cam, pb);
-      }
-      pair_back<KEEP, PINHOLE>(a.cam, a.thr, pa, zu.x, zv.x, zu.y, zv.y, true, left > 1, acc2, n_in, n_out, s0, s1);
-      pair_back<KEEP, PINHOLE>(a.cam, a.thr, pb, zu.z, zv.z, zu.w, zv.w, left > 2, left > 3, acc2, n_in, n_out, s2, s3);
       if (STATUS) {
         if (base + 3 < a.n) {
           *reinterpret_cast<uchar4*>(a.status + base) = make_uchar4(s0, s1, s2, s3);
@@ -485,11 +567,7 @@ __global__ void __launch_bounds__(kLinThreads, kCtasPerSm) picp_linearize_kernel
     }
     float acc[29];
 #pragma unroll
-    for (int i = 0; i < 29; ++i) {
-      float lo, hi;
-      unpack2(acc2[i], lo, hi);
-      acc[i] = lo + hi;
-    }
+    for (int i = 0; i < 29; ++i) acc[i] = picp_slot_total<PINHOLE>(acc2, i);
     // ---- pass 1: warp shuffle tree, then warps summed in warp order
 #pragma unroll
     for (int i = 0; i < 29; ++i) acc[i] = warp_sum(acc[i]);
@@ -795,6 +873,8 @@ __global__ void __launch_bounds__(kResThreads, 1) picp_resident_kernel(const Res
   const long long qb = (long long)blockIdx.x * qpc;
   const long long qe = (qb + qpc < n_quads) ? qb + qpc : n_quads;
   const int nq = qe > qb ? (int)(qe - qb) : 0;
+  // quads with four valid points: all but the last quad of the set when n is not a multiple of 4
+  const int nq_full = (nq > 0 && qe == n_quads && (a.n & 3)) ? nq - 1 : nq;
   const bool peers = a.peer_n > 1;
 
   // ---- gather once: (first: image index, second: world index) -> the CTA's planes in shared memory
@@ -846,29 +926,24 @@ __global__ void __launch_bounds__(kResThreads, 1) picp_resident_kernel(const Res
 #pragma unroll
     for (int i = 0; i < 29; ++i) acc2[i] = 0ull;
     int n_in = 0, n_out = 0;
-    for (int l = tid; l < nq; l += kResThreads) {
+    for (int l = tid; l < nq_full; l += kResThreads) {
       const float4 wx = s_pl[l], wy = s_pl[qpc + l], wz = s_pl[2 * qpc + l], zu = s_pl[3 * qpc + l], zv = s_pl[4 * qpc + l];
-      const long long left = a.n - (qb + l) * 4;  // >= 1; < 4 only in the last quad of the set
       int s0, s1, s2, s3;
-      PairState pa, pb;
-      pair_front<PINHOLE>(a.cam, T, wx.x, wy.x, wz.x, wx.y, wy.y, wz.y, pa);
-      pair_front<PINHOLE>(a.cam, T, wx.z, wy.z, wz.z, wx.w, wy.w, wz.w, pb);
-      if (pa.fix0 || pa.fix1 || pb.fix0 || pb.fix1) {
-        pair_fix(a.cam, pa);
-        pair_fix(a.cam, pb);
-      }
-      pair_back<KEEP, PINHOLE>(a.cam, a.thr, pa, zu.x, zv.x, zu.y, zv.y, true, left > 1, acc2, n_in, n_out, s0, s1);
-      pair_back<KEEP, PINHOLE>(a.cam, a.thr, pb, zu.z, zv.z, zu.w, zv.w, left > 2, left > 3, acc2, n_in, n_out, s2, s3);
+      picp_quad<KEEP, PINHOLE>(a.cam, T, a.thr, wx, wy, wz, zu, zv, true, true, true, acc2, n_in, n_out, s0, s1, s2, s3);
+    }
+    if (nq_full < nq && nq_full % kResThreads == tid) {  // the partial last quad of the set: the last quad of its thread
+      const int l = nq_full;
+      const float4 wx = s_pl[l], wy = s_pl[qpc + l], wz = s_pl[2 * qpc + l], zu = s_pl[3 * qpc + l], zv = s_pl[4 * qpc + l];
+      const long long left = a.n - (qb + l) * 4;  // 1..3
+      int s0, s1, s2, s3;
+      picp_quad<KEEP, PINHOLE>(a.cam, T, a.thr, wx, wy, wz, zu, zv, left > 1, left > 2, left > 3, acc2, n_in, n_out, s0, s1,
+                               s2, s3);
     }
     // ---- warp reduction: lane L ends up with the warp's total of term L (counts are exact in float: < 2^24)
     {
       float v[32];
 #pragma unroll
-      for (int i = 0; i < 29; ++i) {
-        float lo, hi;
-        unpack2(acc2[i], lo, hi);
-        v[i] = lo + hi;
-      }
+      for (int i = 0; i < 29; ++i) v[i] = picp_slot_total<PINHOLE>(acc2, i);
       v[29] = (float)n_in;
       v[30] = (float)n_out;
       v[31] = 0.f;
@@ -952,7 +1027,7 @@ __global__ void __launch_bounds__(kLinThreads, 1) picp_stream_rounds_kernel(cons
   }
   if (tid < 12) s_pose[tid] = a.dev->pose[tid];
   __syncthreads();
-  const long long n_tiles = (a.n + kTile - 1) / kTile;
+  const long long n_tiles = (a.n + kTile - 1) / kTile, n_full_tiles = a.n / kTile;
 
   if (warp == kWarps) {
     // ---------------- producer: one elected lane streams every round's tiles through the ring
@@ -1003,7 +1078,12 @@ __global__ void __launch_bounds__(kLinThreads, 1) picp_stream_rounds_kernel(cons
   RoundCtx rc;
   rc.dev = a.dev; rc.ll = a.ll; rc.ll_seq0 = a.ll_seq0; rc.ll_stride = a.ll_stride; rc.damping = a.damping;
   rc.rel_tol = a.rel_tol; rc.peer_n = a.peer_n; rc.peer_rank = a.peer_rank; rc.peers = a.peers;
-  long long it = 0;
+  // ring position of the consumers (carried across the rounds) and this thread's quad slot, as shared-window addresses
+  unsigned stage = 0, phase = 0;
+  const unsigned full_s = smem_u32(s_full), empty_s = smem_u32(s_empty);
+  const unsigned slot_s = smem_u32(s_tiles) + 16u * (unsigned)tid;
+  constexpr unsigned kPlaneBytes = kTile * sizeof(float), kStageBytes = 5 * kPlaneBytes;
+  const int n_tiles_i = (int)n_tiles, n_full_i = (int)n_full_tiles;  // < 2^31 tiles: 3e12 correspondences
   int r = 0;
   for (; r < a.n_rounds; ++r) {
     float T[12];
@@ -1013,44 +1093,47 @@ __global__ void __launch_bounds__(kLinThreads, 1) picp_stream_rounds_kernel(cons
 #pragma unroll
     for (int i = 0; i < 29; ++i) acc2[i] = 0ull;
     int n_in = 0, n_out = 0;
-    for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
-      const int stage = (int)(it % kStages);
-      const unsigned phase = (unsigned)(it / kStages) & 1u;
-      mbar_wait(&s_full[stage], phase);
-      const float4* tile = reinterpret_cast<const float4*>(s_tiles + (size_t)stage * 5 * kTile);
-      const long long base = t * kTile + 4ll * tid;
+    for (int t = blockIdx.x; t < n_tiles_i; t += gridDim.x) {
+      mbar_wait_s(full_s + 8u * stage, phase);
+      const unsigned q = slot_s + stage * kStageBytes;
+      const unsigned empty = empty_s + 8u * stage;
+      if (++stage == kStages) {
+        stage = 0;
+        phase ^= 1u;
+      }
       float4 wx, wy, wz, zu, zv;
-      const bool any = base < a.n;
-      if (any) {
-        wx = tile[tid];
-        wy = tile[kThreads + tid];
-        wz = tile[2 * kThreads + tid];
-        zu = tile[3 * kThreads + tid];
-        zv = tile[4 * kThreads + tid];
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty[stage]);  // values are in registers: hand the stage back
-      if (!any) continue;
       int s0, s1, s2, s3;
-      const long long left = a.n - base;
-      PairState pa, pb;
-      pair_front<PINHOLE>(a.cam, T, wx.x, wy.x, wz.x, wx.y, wy.y, wz.y, pa);
-      pair_front<PINHOLE>(a.cam, T, wx.z, wy.z, wz.z, wx.w, wy.w, wz.w, pb);
-      if (pa.fix0 || pa.fix1 || pb.fix0 || pb.fix1) {
-        pair_fix(a.cam, pa);
-        pair_fix(a.cam, pb);
+      if (t < n_full_i) {  // every tile but the last of the stream: no per-point validity
+        wx = lds128(q);
+        wy = lds128(q + kPlaneBytes);
+        wz = lds128(q + 2 * kPlaneBytes);
+        zu = lds128(q + 3 * kPlaneBytes);
+        zv = lds128(q + 4 * kPlaneBytes);
+        __syncwarp();
+        if (lane == 0) mbar_arrive_s(empty);  // values are in registers: hand the stage back
+        picp_quad<KEEP, PINHOLE>(a.cam, T, a.thr, wx, wy, wz, zu, zv, true, true, true, acc2, n_in, n_out, s0, s1, s2, s3);
+      } else {
+        const long long base = (long long)t * kTile + 4ll * tid;
+        const bool any = base < a.n;
+        if (any) {
+          wx = lds128(q);
+          wy = lds128(q + kPlaneBytes);
+          wz = lds128(q + 2 * kPlaneBytes);
+          zu = lds128(q + 3 * kPlaneBytes);
+          zv = lds128(q + 4 * kPlaneBytes);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive_s(empty);
+        if (!any) continue;
+        const long long left = a.n - base;
+        picp_quad<KEEP, PINHOLE>(a.cam, T, a.thr, wx, wy, wz, zu, zv, left > 1, left > 2, left > 3, acc2, n_in, n_out, s0,
+                                 s1, s2, s3);
       }
-      pair_back<KEEP, PINHOLE>(a.cam, a.thr, pa, zu.x, zv.x, zu.y, zv.y, true, left > 1, acc2, n_in, n_out, s0, s1);
-      pair_back<KEEP, PINHOLE>(a.cam, a.thr, pb, zu.z, zv.z, zu.w, zv.w, left > 2, left > 3, acc2, n_in, n_out, s2, s3);
     }
     {  // warp reduction: lane L ends up with the warp's total of term L (per-warp counts are exact in float)
       float v[32];
 #pragma unroll
-      for (int i = 0; i < 29; ++i) {
-        float lo, hi;
-        unpack2(acc2[i], lo, hi);
-        v[i] = lo + hi;
-      }
+      for (int i = 0; i < 29; ++i) v[i] = picp_slot_total<PINHOLE>(acc2, i);
       v[29] = (float)n_in;
       v[30] = (float)n_out;
       v[31] = 0.f;
