@@ -239,6 +239,10 @@ __device__ __forceinline__ void pair_mid(const PicpCam& cam, float thr, PairStat
   s.odd = s.odd || !(chi0 <= FLT_MAX) || !(chi1 <= FLT_MAX);  // chi is >= 0, +inf or NaN
 }
 
+// the accumulation's multiply-add: packed.  (Two scalar FFMA on the halves - the same two IEEE operations, twice the
+// issue slots, no three-wide-operand register reads - measured 61.2 instead of 47.0 us per round at 10,485,760.)
+__device__ __forceinline__ f2 acc_fma2(f2 a, f2 b, f2 c) { return fma2(a, b, c); }
+
 // stage 4: J, H += w J^T J and b += w J^T e (tolerance part).  ODD: every input of a dropped point is zeroed.
 template <bool KEEP, bool PINHOLE, bool ODD>
 __device__ __forceinline__ void pair_acc(const PicpCam& cam, float thr, const PairState& s, f2 (&acc2)[29]) {
@@ -303,11 +307,11 @@ __device__ __forceinline__ void pair_acc(const PicpCam& cam, float thr, const Pa
 #pragma unroll
     for (int j = i; j < 6; ++j, ++k) {
       const bool y0 = z0 || (PINHOLE && j == 1), y1 = z1 || (PINHOLE && j == 0);
-      if (!y0) acc2[k] = fma2(s0, J0[j], acc2[k]);
-      if (!y1) acc2[k] = fma2(s1, J1[j], acc2[k]);
+      if (!y0) acc2[k] = acc_fma2(s0, J0[j], acc2[k]);
+      if (!y1) acc2[k] = acc_fma2(s1, J1[j], acc2[k]);
     }
-    if (!z0) acc2[21 + i] = fma2(s0, e0, acc2[21 + i]);
-    if (!z1) acc2[21 + i] = fma2(s1, e1, acc2[21 + i]);
+    if (!z0) acc2[21 + i] = acc_fma2(s0, e0, acc2[21 + i]);
+    if (!z1) acc2[21 + i] = acc_fma2(s1, e1, acc2[21 + i]);
   }
 }
 
@@ -328,6 +332,37 @@ __device__ __forceinline__ void picp_quad(const PicpCam& cam, const float* __res
   }
   pair_mid<KEEP>(cam, thr, pa, zu.x, zv.x, zu.y, zv.y, true, v1, acc2, n_in, n_out, s0, s1);
   pair_mid<KEEP>(cam, thr, pb, zu.z, zv.z, zu.w, zv.w, v2, v3, acc2, n_in, n_out, s2, s3);
+  if (pa.odd || pb.odd) {
+    pair_acc<KEEP, PINHOLE, true>(cam, thr, pa, acc2);
+    pair_acc<KEEP, PINHOLE, true>(cam, thr, pb, acc2);
+  } else {
+    pair_acc<KEEP, PINHOLE, false>(cam, thr, pa, acc2);
+    pair_acc<KEEP, PINHOLE, false>(cam, thr, pb, acc2);
+  }
+}
+
+// picp_quad in two halves for a quad with four valid points, so that the resident kernel can put the shared-memory
+// loads of its NEXT quad between them: the loaded values of this quad are dead after stage 3, and the ~110 packed
+// FMAs of stage 4 cover the latency of the loads (1,048,576 correspondences: 6.86 -> 6.82 us per round, 1,310,720:
+// 7.86 -> 7.64).  The streaming kernel does NOT do this: there the early wait on the next tile's barrier costs more
+// than the loads it hides (46.98 -> 50.82 us per round at 10,485,760).
+template <bool KEEP, bool PINHOLE>
+__device__ __forceinline__ void picp_quad_head(const PicpCam& cam, const float* __restrict__ T, float thr, const float4& wx,
+                                               const float4& wy, const float4& wz, const float4& zu, const float4& zv,
+                                               PairState& pa, PairState& pb, f2 (&acc2)[29], int& n_in, int& n_out) {
+  int s0, s1, s2, s3;
+  pair_front<PINHOLE>(cam, T, wx.x, wy.x, wz.x, wx.y, wy.y, wz.y, pa);
+  pair_front<PINHOLE>(cam, T, wx.z, wy.z, wz.z, wx.w, wy.w, wz.w, pb);
+  if (pa.fix0 || pa.fix1 || pb.fix0 || pb.fix1) {
+    pair_fix(cam, pa);
+    pair_fix(cam, pb);
+  }
+  pair_mid<KEEP>(cam, thr, pa, zu.x, zv.x, zu.y, zv.y, true, true, acc2, n_in, n_out, s0, s1);
+  pair_mid<KEEP>(cam, thr, pb, zu.z, zv.z, zu.w, zv.w, true, true, acc2, n_in, n_out, s2, s3);
+}
+template <bool KEEP, bool PINHOLE>
+__device__ __forceinline__ void picp_quad_tail(const PicpCam& cam, float thr, const PairState& pa, const PairState& pb,
+                                               f2 (&acc2)[29]) {
   if (pa.odd || pb.odd) {
     pair_acc<KEEP, PINHOLE, true>(cam, thr, pa, acc2);
     pair_acc<KEEP, PINHOLE, true>(cam, thr, pb, acc2);
@@ -926,10 +961,21 @@ __global__ void __launch_bounds__(kResThreads, 1) picp_resident_kernel(const Res
 #pragma unroll
     for (int i = 0; i < 29; ++i) acc2[i] = 0ull;
     int n_in = 0, n_out = 0;
-    for (int l = tid; l < nq_full; l += kResThreads) {
-      const float4 wx = s_pl[l], wy = s_pl[qpc + l], wz = s_pl[2 * qpc + l], zu = s_pl[3 * qpc + l], zv = s_pl[4 * qpc + l];
-      int s0, s1, s2, s3;
-      picp_quad<KEEP, PINHOLE>(a.cam, T, a.thr, wx, wy, wz, zu, zv, true, true, true, acc2, n_in, n_out, s0, s1, s2, s3);
+    {  // each quad is loaded one step ahead, between stages 3 and 4 of the quad before it (picp_quad_head / _tail)
+      int l = tid;
+      float4 wx, wy, wz, zu, zv;
+      if (l < nq_full) {
+        wx = s_pl[l]; wy = s_pl[qpc + l]; wz = s_pl[2 * qpc + l]; zu = s_pl[3 * qpc + l]; zv = s_pl[4 * qpc + l];
+      }
+      while (l < nq_full) {
+        PairState pa, pb;
+        picp_quad_head<KEEP, PINHOLE>(a.cam, T, a.thr, wx, wy, wz, zu, zv, pa, pb, acc2, n_in, n_out);
+        l += kResThreads;
+        if (l < nq_full) {
+          wx = s_pl[l]; wy = s_pl[qpc + l]; wz = s_pl[2 * qpc + l]; zu = s_pl[3 * qpc + l]; zv = s_pl[4 * qpc + l];
+        }
+        picp_quad_tail<KEEP, PINHOLE>(a.cam, a.thr, pa, pb, acc2);
+      }
     }
     if (nq_full < nq && nq_full % kResThreads == tid) {  // the partial last quad of the set: the last quad of its thread
       const int l = nq_full;
