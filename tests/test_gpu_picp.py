@@ -123,6 +123,67 @@ def test_linearize_adversarial_sweep(ctx, oracle, seed):
             assert not (np.isfinite(lin["H"]).all() and np.isfinite(lin["b"]).all()), tag
 
 
+@pytest.mark.parametrize("keep", [False, True])
+def test_dropped_points_with_non_finite_terms_leave_the_sums_finite(ctx, oracle, keep):
+    """A point that does not contribute is removed by zeroing its 1/z alone - exact only while its other terms are
+    finite.  Points that are dropped AND carry non-finite terms (coordinates around 3e38 whose K c overflows: skipped;
+    an inf measurement: - without keep_outliers - a rejected outlier) must take the zero-everything accumulation:
+    the statuses are the oracle's and H, b stay finite and within 1e-4 of the oracle's, in linearize and in all three
+    round kernels; sprinkled so that every quad position and both pairs of a quad are hit."""
+    fr = synth.picp_frame(n=6000, seed=77)
+    world, image = fr["world"].copy(), fr["image"].copy()
+    # finite coordinates whose q = K c overflows (an inf coordinate would turn into a NaN depth through 0 * inf and
+    # poison the reference's system as an inlier: that case is in the adversarial sweep above)
+    bad_world = np.array([[3e38, 0, 5], [-3e38, 1, 5], [0, 3e38, 5], [2e38, 2e38, 5], [1, 1, -3e38], [3e38, 3e38, -3e38],
+                          [1e37, -1e37, 1e-3]], np.float32)
+    for j, k in enumerate(range(3, 6000, 97)):
+        world[fr["pairs"][k, 1]] = bad_world[(j + k) % len(bad_world)]
+    for k in range(50, 6000, 211):  # a finite projection against an infinite measurement: chi = inf > thr
+        image[fr["pairs"][k, 0], k % 2] = np.inf if k % 3 else -np.inf
+    thr = 3000.0
+    ref = oracle.linearize(fr["K"], fr["rows"], fr["cols"], fr["pose0"], world, image, fr["pairs"], thr, keep, accum="f64")
+    with np.errstate(all="ignore"):
+        ref_finite = np.isfinite(ref["H"]).all() and np.isfinite(ref["b"]).all()
+    assert ref_finite == (not keep)  # a KEPT outlier with chi = inf poisons the reference's system (lambda = 0, e = inf)
+    s = ctx.picp()
+    s.set_camera(fr["K"], fr["rows"], fr["cols"], fr["pose0"])
+    s.set_points(world, image)
+    s.set_correspondences(fr["pairs"])
+    lin = s.linearize(thr, keep, want_status=True, n_pairs=len(fr["pairs"]))
+    assert np.array_equal(lin["status"], ref["status"])
+    assert (ref["status"] == 0).sum() >= 60 and (ref["status"] == 2).sum() >= 20
+    assert lin["n_inliers"] == ref["n_inliers"] and lin["n_outliers"] == int((ref["status"] == 2).sum())
+    if ref_finite:
+        assert np.isfinite(lin["H"]).all() and np.isfinite(lin["b"]).all()
+        assert np.abs(lin["H"] - ref["H"]).max() <= H_TOL * np.abs(ref["H"]).max()
+        assert np.abs(lin["b"] - ref["b"]).max() <= H_TOL * np.abs(ref["b"]).max()
+        assert abs(lin["chi_in"] - ref["chi_in"]) <= H_TOL * max(ref["chi_in"], 1.0)
+        assert lin["chi_out"] == np.inf
+    else:
+        assert not (np.isfinite(lin["H"]).all() and np.isfinite(lin["b"]).all())
+    s.close()
+    if not ref_finite:
+        return
+    poses = []
+    for mode in (1, 2, 3):  # per-round launches, shared-memory resident, persistent streaming
+        s = ctx.picp()
+        s.set_mode(mode)
+        s.set_camera(fr["K"], fr["rows"], fr["cols"], fr["pose0"])
+        s.set_points(world, image)
+        s.set_correspondences(fr["pairs"])
+        s.enqueue_rounds(thr, 1.0, keep, 4)
+        st = s.fetch_stats(4)
+        assert st[0].num_inliers == ref["n_inliers"], mode
+        poses.append(s.get_pose())
+        assert np.isfinite(poses[-1]).all(), mode
+        s.close()
+    pose = np.array(fr["pose0"], np.float32)
+    for _ in range(4):
+        pose, _, _, _ = oracle.one_round(fr["K"], fr["rows"], fr["cols"], pose, world, image, fr["pairs"], thr, 1.0, keep)
+    for q in poses:
+        assert np.abs(q - pose).max() <= POSE_TOL
+
+
 def test_mask_on_threshold_knife_edge(ctx, oracle):
     """Measurements placed so that chi lands within a few ulps of the kernel threshold for EVERY
     correspondence: the inlier mask then depends on the last bit of the projection (the kernel's
