@@ -721,6 +721,8 @@ struct ResArgs {
   int ll_stride;
   int peer_n, peer_rank;
   VoMailbox* peers[VO_MAX_PEERS];
+  int use_pose0;     // start from pose0 (a vo_picp_set_pose not yet on the device) instead of dev->pose
+  float pose0[12];
 };
 
 __device__ __forceinline__ unsigned long long ld_poll(const unsigned long long* p) {
@@ -945,7 +947,7 @@ __global__ void __launch_bounds__(kResThreads, 1) picp_resident_kernel(const Res
     }
     if (bad) a.dev->bad_index = 1;
   }
-  if (tid < 12) s_pose[tid] = a.dev->pose[tid];
+  if (tid < 12) s_pose[tid] = a.use_pose0 ? a.pose0[tid] : a.dev->pose[tid];
   if (tid == 0) s_stop = 0;
   VoMailbox* me = peers ? a.peers[a.peer_rank] : nullptr;
   const unsigned mb_seq0 = peers ? *(volatile unsigned*)&me->seq : 0u;
@@ -1037,6 +1039,8 @@ struct StreamArgs {
   int ll_stride;
   int peer_n, peer_rank;
   VoMailbox* peers[VO_MAX_PEERS];
+  int use_pose0;  // as in ResArgs
+  float pose0[12];
 };
 
 __device__ __forceinline__ bool mbar_try_wait_hint(unsigned long long* bar, unsigned parity) {
@@ -1071,7 +1075,7 @@ __global__ void __launch_bounds__(kLinThreads, 1) picp_stream_rounds_kernel(cons
     s_stop = 0;
     s_round_done = 0;
   }
-  if (tid < 12) s_pose[tid] = a.dev->pose[tid];
+  if (tid < 12) s_pose[tid] = a.use_pose0 ? a.pose0[tid] : a.dev->pose[tid];
   __syncthreads();
   const long long n_tiles = (a.n + kTile - 1) / kTile, n_full_tiles = a.n / kTile;
 
@@ -1354,9 +1358,23 @@ struct vo_picp {
   unsigned long long* d_ll = nullptr;    // resident kernel: [2][kResMaxGrid][32] self-validating words
   unsigned ll_seq = 0;                   // sequence number of the last round exchanged through d_ll
   int mode = VO_PICP_MODE_AUTO;
+  // vo_picp_set_pose only records the pose: the persistent kernels take it as a launch argument (one tiny kernel and
+  // one launch gap less per frame), every other reader of dev->pose flushes it first (flush_pose)
+  bool pose_pending = false;
+  float h_pose[12] = {0};
 };
 
 namespace {
+
+int flush_pose(vo_picp* s) {
+  if (!s->pose_pending) return VO_OK;
+  PoseArg a;
+  memcpy(a.p, s->h_pose, sizeof(a.p));
+  picp_set_pose_kernel<<<1, 32, 0, s->ctx->stream>>>(s->d_dev, a);
+  VO_CHECK_LAUNCH(s->ctx, "picp_set_pose_kernel");
+  s->pose_pending = false;
+  return VO_OK;
+}
 
 int grow(vo_ctx* ctx, void** p, size_t* cap, size_t bytes) {
   if (bytes <= *cap) return VO_OK;
@@ -1419,6 +1437,8 @@ int ensure_packed(vo_picp* s) {
 int launch_linearize(vo_picp* s, float thr, float damping, bool keep, bool status, bool fuse_solve) {
   vo_ctx* ctx = s->ctx;
   int st = ensure_packed(s);
+  if (st) return st;
+  st = flush_pose(s);  // this kernel reads dev->pose
   if (st) return st;
   LinArgs a;
   a.pk = s->d_pk;
@@ -1514,6 +1534,9 @@ int launch_resident(vo_picp* s, const ResPlan& pl, float thr, float damping, boo
   a.peer_n = ctx->peer_n > 1 ? ctx->peer_n : 0;
   a.peer_rank = ctx->peer_rank;
   for (int p = 0; p < VO_MAX_PEERS; ++p) a.peers[p] = (VoMailbox*)ctx->peer_mailbox[p];
+  a.use_pose0 = s->pose_pending ? 1 : 0;  // (the kernel leaves the final pose in dev->pose either way)
+  memcpy(a.pose0, s->h_pose, sizeof(a.pose0));
+  s->pose_pending = false;
   s->ll_seq += (unsigned)n_rounds;
   cudaError_t e;
   if (keep) e = s->pinhole ? launch_res2<true, true>(pl, ctx->stream, a) : launch_res2<true, false>(pl, ctx->stream, a);
@@ -1571,6 +1594,9 @@ int launch_stream_rounds(vo_picp* s, float thr, float damping, bool keep, int n_
   a.peer_n = ctx->peer_n > 1 ? ctx->peer_n : 0;
   a.peer_rank = ctx->peer_rank;
   for (int p = 0; p < VO_MAX_PEERS; ++p) a.peers[p] = (VoMailbox*)ctx->peer_mailbox[p];
+  a.use_pose0 = s->pose_pending ? 1 : 0;  // (the kernel leaves the final pose in dev->pose either way)
+  memcpy(a.pose0, s->h_pose, sizeof(a.pose0));
+  s->pose_pending = false;
   s->ll_seq += (unsigned)n_rounds;
   int grid = grid_for(s);
   if (grid > kResMaxGrid) grid = kResMaxGrid;
@@ -1667,18 +1693,16 @@ int vo_picp_destroy(vo_picp* s) {
 
 int vo_picp_set_pose(vo_picp* s, const float pose[12]) {
   if (!s || !pose) return VO_ERR_INVALID;
-  int st = vo_ctx_activate(s->ctx);
-  if (st) return st;
-  PoseArg a;
-  memcpy(a.p, pose, sizeof(a.p));
-  picp_set_pose_kernel<<<1, 32, 0, s->ctx->stream>>>(s->d_dev, a);
-  VO_CHECK_LAUNCH(s->ctx, "picp_set_pose_kernel");
+  memcpy(s->h_pose, pose, sizeof(s->h_pose));  // reaches the device with the next kernel that reads the pose
+  s->pose_pending = true;
   return VO_OK;
 }
 
 int vo_picp_get_pose(vo_picp* s, float pose[12]) {
   if (!s || !pose) return VO_ERR_INVALID;
   int st = vo_ctx_activate(s->ctx);
+  if (st) return st;
+  st = flush_pose(s);
   if (st) return st;
   void* h;
   st = vo_pinned(s->ctx, 64, &h);
