@@ -115,7 +115,9 @@ int vo_picp_create(vo_ctx* ctx, vo_picp** out);                 /* PICPSolver() 
 int vo_picp_destroy(vo_picp* s);
 /* init(camera, ...) copies the Camera by value (picp_solver.cpp:17-23; camera.cpp:4-11) */
 int vo_picp_set_camera(vo_picp* s, const float K[9], int rows, int cols, const float pose[12]);
-int vo_picp_set_pose(vo_picp* s, const float pose[12]);         /* Camera::setWorldInCameraPose */
+/* Camera::setWorldInCameraPose. Host-side only: the pose is copied and reaches the device in stream order with the next
+ * call that reads it (as a launch argument of the persistent solve kernels, otherwise through a one-warp kernel). */
+int vo_picp_set_pose(vo_picp* s, const float pose[12]);
 int vo_picp_get_pose(vo_picp* s, float pose[12]);               /* camera().worldInCameraPose() */
 /* init(..., world_points, image_points): uploads (copies) the points. The reference keeps raw
  * pointers (picp_solver.cpp:21-22), which dangle in exec/icp_test.cpp:81-85; copying is the
