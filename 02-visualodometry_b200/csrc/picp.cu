@@ -1077,17 +1077,25 @@ __global__ void __launch_bounds__(kLinThreads, 1) picp_stream_rounds_kernel(cons
   }
   if (tid < 12) s_pose[tid] = a.use_pose0 ? a.pose0[tid] : a.dev->pose[tid];
   __syncthreads();
-  const long long n_tiles = (a.n + kTile - 1) / kTile, n_full_tiles = a.n / kTile;
+  // This CTA's share: a contiguous range of quads, the same for every CTA to within one quad (tiles dealt out round
+  // robin leave 47 of 148 CTAs with 51 tiles and the rest with 50 at 10,485,760 correspondences - and 26 / 25, 13 / 12
+  // on a 2- / 4-GPU shard - and every round ends when the longest CTA does).  The range is cut into tiles of kTile
+  // correspondences; only its last tile can be short.
+  const long long n_quads = (a.n + 3) >> 2;
+  const long long c_begin = 4 * ((long long)blockIdx.x * n_quads / gridDim.x);
+  const long long c_end = 4 * ((long long)(blockIdx.x + 1) * n_quads / gridDim.x);  // (padded to whole quads)
+  const int my_tiles = (int)((c_end - c_begin + kTile - 1) / kTile);
+  const long long c_lim = c_end < a.n ? c_end : a.n;  // the valid correspondences of the range end here
 
   if (warp == kWarps) {
     // ---------------- producer: one elected lane streams every round's tiles through the ring
     if (lane != 0) return;
     long long it = 0;
     bool aborted = false;
-    auto issue = [&](long long t, long long i) {
+    auto issue = [&](int j, long long i) {
       const int stage = (int)(i % kStages);
-      const long long first = t * kTile;
-      const long long left = ((a.n + 3) & ~3ll) - first;
+      const long long first = c_begin + (long long)j * kTile;
+      const long long left = c_end - first;
       const unsigned bytes = (unsigned)((left < kTile ? left : kTile) * sizeof(float));
       float* dst = s_tiles + (size_t)stage * 5 * kTile;
       mbar_arrive_expect_tx(&s_full[stage], 5u * bytes);
@@ -1099,7 +1107,7 @@ __global__ void __launch_bounds__(kLinThreads, 1) picp_stream_rounds_kernel(cons
         while (*(volatile int*)&s_round_done < r && *(volatile int*)&s_stop != 2) {}
         if (*(volatile int*)&s_stop) break;
       }
-      for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+      for (int j = 0; j < my_tiles; ++j, ++it) {
         if (it >= kStages) {
           const int stage = (int)(it % kStages);
           const unsigned phase = (unsigned)(it / kStages) & 1u;
@@ -1111,7 +1119,7 @@ __global__ void __launch_bounds__(kLinThreads, 1) picp_stream_rounds_kernel(cons
           }
           if (aborted) break;
         }
-        issue(t, it);
+        issue(j, it);
       }
     }
     if (aborted) {  // copies in flight must land before the CTA may exit
@@ -1133,7 +1141,7 @@ __global__ void __launch_bounds__(kLinThreads, 1) picp_stream_rounds_kernel(cons
   const unsigned full_s = smem_u32(s_full), empty_s = smem_u32(s_empty);
   const unsigned slot_s = smem_u32(s_tiles) + 16u * (unsigned)tid;
   constexpr unsigned kPlaneBytes = kTile * sizeof(float), kStageBytes = 5 * kPlaneBytes;
-  const int n_tiles_i = (int)n_tiles, n_full_i = (int)n_full_tiles;  // < 2^31 tiles: 3e12 correspondences
+  const int n_full_i = (int)((c_lim - c_begin) / kTile);  // tiles of this CTA with kTile valid correspondences
   int r = 0;
   for (; r < a.n_rounds; ++r) {
     float T[12];
@@ -1143,7 +1151,7 @@ __global__ void __launch_bounds__(kLinThreads, 1) picp_stream_rounds_kernel(cons
 #pragma unroll
     for (int i = 0; i < 29; ++i) acc2[i] = 0ull;
     int n_in = 0, n_out = 0;
-    for (int t = blockIdx.x; t < n_tiles_i; t += gridDim.x) {
+    for (int t = 0; t < my_tiles; ++t) {
       mbar_wait_s(full_s + 8u * stage, phase);
       const unsigned q = slot_s + stage * kStageBytes;
       const unsigned empty = empty_s + 8u * stage;
@@ -1153,7 +1161,7 @@ __global__ void __launch_bounds__(kLinThreads, 1) picp_stream_rounds_kernel(cons
       }
       float4 wx, wy, wz, zu, zv;
       int s0, s1, s2, s3;
-      if (t < n_full_i) {  // every tile but the last of the stream: no per-point validity
+      if (t < n_full_i) {  // every tile but the last of the range: no per-point validity
         wx = lds128(q);
         wy = lds128(q + kPlaneBytes);
         wz = lds128(q + 2 * kPlaneBytes);
@@ -1163,8 +1171,8 @@ __global__ void __launch_bounds__(kLinThreads, 1) picp_stream_rounds_kernel(cons
         if (lane == 0) mbar_arrive_s(empty);  // values are in registers: hand the stage back
         picp_quad<KEEP, PINHOLE>(a.cam, T, a.thr, wx, wy, wz, zu, zv, true, true, true, acc2, n_in, n_out, s0, s1, s2, s3);
       } else {
-        const long long base = (long long)t * kTile + 4ll * tid;
-        const bool any = base < a.n;
+        const long long base = c_begin + (long long)t * kTile + 4ll * tid;
+        const bool any = base < c_lim;
         if (any) {
           wx = lds128(q);
           wy = lds128(q + kPlaneBytes);
@@ -1175,7 +1183,7 @@ __global__ void __launch_bounds__(kLinThreads, 1) picp_stream_rounds_kernel(cons
         __syncwarp();
         if (lane == 0) mbar_arrive_s(empty);
         if (!any) continue;
-        const long long left = a.n - base;
+        const long long left = c_lim - base;  // < 4 only in the last quad of the whole set
         picp_quad<KEEP, PINHOLE>(a.cam, T, a.thr, wx, wy, wz, zu, zv, left > 1, left > 2, left > 3, acc2, n_in, n_out, s0,
                                  s1, s2, s3);
       }
