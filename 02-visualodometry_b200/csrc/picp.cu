@@ -132,7 +132,7 @@ __device__ __forceinline__ f2 rcp2_newton(f2 z, float z0, float z1) {
 //  * no negated copies of c: the pinhole Jacobian is built from -g, -h and -fx/z, which turns columns 2 and 3 of BOTH
 //    rows into their exact negatives; round-to-nearest is sign-symmetric, so the affected sums (H[i][j] with exactly
 //    one index in {2,3}; b[2], b[3]) are the exact negatives of the true ones and are flipped back once per round
-//    where the packed accumulators are unpacked (picp_slot_sign).
+//    where the packed accumulators are unpacked (picp_slot_flipped, picp_slot_total).
 //  * the inlier / outlier counters are predicated adds, chi sums are plain packed adds of the selected chi.
 struct PairState {
   f2 c0, c1, c2, q0, q1, iz, e0, e1, chi;
